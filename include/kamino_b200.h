@@ -1,0 +1,184 @@
+/*
+ * kamino_b200.h -- C ABI of the B200-native (sm_100a) implementation of KaminoGPU's
+ * per-timestep solver path (advection -> geometric -> projection, plus tracer particles).
+ *
+ * The reference has no FFI: its boundary for this path is the C++ class surface
+ * KaminoSolver / KaminoQuantity / KaminoParticles / Kamino (paths below are relative to
+ * /root/reference/KaminoGPU/). The C++ host classes in kaminogpu_b200/host/ keep that
+ * surface and call ONLY the functions declared here; Python (ctypes) binds the same
+ * symbols for tests and bench.py. Plain pointers and sizes only -- no CUDA or torch
+ * types cross this boundary (streams are passed as void*).
+ *
+ * Conventions: every function returns 0 on success, otherwise a non-zero code
+ * (a cudaError_t value, or one of KAMINO_ERR_*); kamino_last_error() returns the text.
+ * No exceptions, no process-global solver state, no cudaDeviceReset: several contexts
+ * may coexist in one process (unlike the reference, include/KaminoSolver.cuh:6-112,
+ * whose kernels read file-static __constant__ parameters, kernel/KaminoCore.cu:5-9).
+ * A context is not thread-safe; use one context per host thread.
+ *
+ * Grid: nPhi = 2 * nTheta (kernel/KaminoCore.cu:849), nTheta a power of two >= 16.
+ * Field layouts (row-major, row = theta index j, column = phi index i, dense pitch nPhi):
+ *   KAMINO_VEL_PHI    nTheta     x nPhi   node (phi=(i-1/2)h, theta=(j+1/2)h)
+ *   KAMINO_VEL_THETA  (nTheta-1) x nPhi   node (phi=i h,      theta=(j+1)h)
+ *   KAMINO_DENSITY    nTheta     x nPhi   node (phi=i h,      theta=(j+1/2)h)
+ *   KAMINO_PRESSURE   nTheta     x nPhi   same nodes as density
+ * Particles: numParticles x (phi, theta) interleaved fp32 (kernel/KaminoParticles.cu:59-62).
+ * A context may hold `batch` independent simulations of the same shape (ensembles);
+ * `sim` selects one.
+ */
+#ifndef KAMINO_B200_H
+#define KAMINO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kamino_ctx kamino_ctx;
+
+enum {
+    KAMINO_VEL_PHI = 0,
+    KAMINO_VEL_THETA = 1,
+    KAMINO_DENSITY = 2,
+    KAMINO_PRESSURE = 3
+};
+
+enum {
+    KAMINO_ERR_INVALID = 10001,   /* bad argument */
+    KAMINO_ERR_NO_DEVICE = 10002, /* no CUDA device / not an sm_100 part */
+    KAMINO_ERR_STATE = 10003      /* call not valid in the current state */
+};
+
+/* sampler kinds for kamino_debug_locate: sampleVPhi / sampleVTheta / sampleCentered,
+ * kernel/KaminoCore.cu:36-184 */
+enum { KAMINO_SAMPLE_VPHI = 0, KAMINO_SAMPLE_VTHETA = 1, KAMINO_SAMPLE_CENTERED = 2 };
+
+/* ---- lifetime -------------------------------------------------------------------- */
+
+/* Replaces the KaminoSolver constructor's device work (kernel/KaminoSolver.cu:12-67:
+ * cudaSetDevice, ten cudaMalloc, precomputeABCCoef, four KaminoQuantity, cufftPlanMany)
+ * and the constant uploads of Kamino::run (kernel/KaminoCore.cu:868-872). `dt` is the
+ * value the reference uploads as timeStepGlobal (the kernels ignore stepForward's
+ * argument, kernel/KaminoSolver.cu:199). particlesPerSim may be 0. */
+int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float dt,
+                  int batch, long particlesPerSim);
+
+/* KaminoSolver::initParticlesfromPic (kernel/KaminoSolver.cu:279-282) creates the particle
+ * set after the solver exists: (re)allocate the particle double buffer for
+ * particlesPerSim particles per simulation (contents zeroed; upload afterwards). */
+int kamino_alloc_particles(kamino_ctx* ctx, long particlesPerSim);
+
+/* Replaces ~KaminoSolver (kernel/KaminoSolver.cu:69-104) without the cudaDeviceReset. */
+int kamino_destroy(kamino_ctx* ctx);
+
+/* Text of the last error of this context (or of the last failed kamino_create when
+ * ctx is NULL). Never NULL. */
+const char* kamino_last_error(const kamino_ctx* ctx);
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream). Invalidates captured step graphs. */
+int kamino_set_stream(kamino_ctx* ctx, void* cudaStream);
+
+/* Shape queries. */
+int kamino_get_shape(const kamino_ctx* ctx, int* nTheta, int* nPhi, int* batch, long* particlesPerSim);
+
+/* ---- state transfer ---------------------------------------------------------------- */
+
+/* KaminoQuantity::copyToGPU / copyBackToCPU (kernel/KaminoQuantity.cu:3-18): dense host
+ * array (rows x nPhi floats) <-> the "this step" device buffer of `field` of simulation
+ * `sim`. Synchronous with respect to the host buffer. */
+int kamino_upload_field(kamino_ctx* ctx, int field, int sim, const float* host);
+int kamino_download_field(kamino_ctx* ctx, int field, int sim, float* host);
+
+/* KaminoParticles::copy2GPU / copyBack2CPU (kernel/KaminoParticles.cu:94-110). */
+int kamino_upload_particles(kamino_ctx* ctx, int sim, const float* hostPhiTheta);
+int kamino_download_particles(kamino_ctx* ctx, int sim, float* hostPhiTheta);
+
+/* Asynchronous variants for pinned host memory (used by the end-to-end frame loop);
+ * completion is observed with kamino_sync. */
+int kamino_download_field_async(kamino_ctx* ctx, int field, int sim, float* pinnedHost);
+int kamino_download_particles_async(kamino_ctx* ctx, int sim, float* pinnedHost);
+int kamino_upload_field_async(kamino_ctx* ctx, int field, int sim, const float* pinnedHost);
+int kamino_upload_particles_async(kamino_ctx* ctx, int sim, const float* pinnedHost);
+
+/* KaminoQuantity::getGPUThisStep / getGPUNextStep / get*PitchInElements
+ * (include/KaminoQuantity.cuh:60-66): raw device pointer of the current this/next buffer
+ * (which = 0 / 1) and its pitch in elements. The pointers swap after every phase exactly
+ * as the reference's do. */
+int kamino_field_device_ptr(kamino_ctx* ctx, int field, int sim, int which,
+                            void** devicePtr, size_t* pitchInElements);
+/* KaminoParticles::coordGPUThisStep / coordGPUNextStep (include/KaminoParticles.cuh:18-19). */
+int kamino_particles_device_ptr(kamino_ctx* ctx, int sim, int which, void** devicePtr);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+
+/* KaminoSolver::advection (kernel/KaminoCore.cu:344-384): u_phi, u_theta, density and the
+ * particles are advected with the pre-advection velocity; buffers swap. */
+int kamino_advect(kamino_ctx* ctx);
+/* KaminoSolver::geometric (kernel/KaminoCore.cu:551-583). */
+int kamino_geometric(kamino_ctx* ctx);
+/* KaminoSolver::projection (kernel/KaminoCore.cu:749-842); leaves the pressure in
+ * KAMINO_PRESSURE. */
+int kamino_project(kamino_ctx* ctx);
+
+/* KaminoSolver::stepForward (kernel/KaminoSolver.cu:197-221) nSteps times, launched as
+ * CUDA graphs on the context's stream. Asynchronous: returns once the work is queued. */
+int kamino_step(kamino_ctx* ctx, int nSteps);
+
+/* Block the host until all queued work of this context is complete. */
+int kamino_sync(kamino_ctx* ctx);
+
+/* Kamino::run's frame loop (kernel/KaminoCore.cu:886-904) with output to host memory
+ * instead of .bgeo files: for each of nFrames frames, stepsPerFrame steps followed by
+ * the read-backs the reference's writers perform (velPhi, velTheta, density and particle
+ * coordinates of every simulation, kernel/KaminoSolver.cu:301-303,375) into the given
+ * pinned host buffers (each sized for all `batch` simulations, any may be NULL to skip).
+ * Synchronous. */
+int kamino_run_frames(kamino_ctx* ctx, int nFrames, int stepsPerFrame,
+                      float* hostVelPhi, float* hostVelTheta, float* hostDensity,
+                      float* hostParticles);
+
+/* Per-phase accumulated device time in seconds since creation / last reset: the
+ * reference's advectionTime / geometricTime / projectionTime (kernel/KaminoSolver.cu:201-218).
+ * Only kamino_advect / kamino_geometric / kamino_project accumulate (graph-launched steps
+ * are not split by phase). */
+int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, float* projection, int reset);
+
+/* Number of kernel launches one kamino_step(ctx, 1) performs (for bench.py's gpu_launches). */
+int kamino_launches_per_step(const kamino_ctx* ctx);
+
+/* ---- host-side initialisers (pure CPU; reproduce the reference's initial state) ------ */
+
+/* KaminoSolver::initialize_velocity (kernel/KaminoInitializer.cu:3-134): FBM curl-noise
+ * initial u_phi (nTheta x nPhi) and u_theta ((nTheta-1) x nPhi). */
+int kamino_init_velocity_host(int nTheta, float radius, float* velPhi, float* velTheta);
+/* KaminoParticles constructor (kernel/KaminoParticles.cu:20-62): particle count for a
+ * density, and the jittered lattice driven by libc rand() in the reference's call order
+ * (the generator is put into its never-seeded state first). */
+long kamino_particle_count(int nTheta, float particleDensity);
+int kamino_seed_particles_host(int nTheta, float particleDensity, float* coords);
+
+/* ---- parity instrumentation ------------------------------------------------------------ */
+
+/* Evaluate, on the device, the index / predicate part of the reference's samplers
+ * (kernel/KaminoCore.cu:36-53, 86-103, 136-153) for n raw coordinates: cell indices
+ * before the modulo, interpolation weights, validated coordinates and flags
+ * (bit 0 = validateCoord returned -1, bit 1 = pole branch taken). Host arrays. */
+int kamino_debug_locate(kamino_ctx* ctx, int kind, long n, const float* phiRaw, const float* thetaRaw,
+                        int32_t* phiIndex, int32_t* thetaIndex, float* alphaPhi, float* alphaTheta,
+                        float* phiValidated, float* thetaValidated, int32_t* flags);
+
+/* Library build information: "kamino_b200 <version> sm_100a". */
+const char* kamino_version(void);
+
+/* Allocate / free page-locked host memory (for the asynchronous transfer entry points). */
+int kamino_host_alloc(void** ptr, size_t bytes);
+int kamino_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* KAMINO_B200_H */

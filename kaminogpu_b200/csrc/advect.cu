@@ -1,0 +1,173 @@
+// Semi-Lagrangian advection of u_phi, u_theta, density and the tracer particles.
+//
+// Replaces advectionVPhiKernel / advectionVThetaKernel / advectionCentered /
+// advectionParticles and KaminoSolver::advection (kernel/KaminoCore.cu:186-384): four
+// launches and two device syncs become ONE launch whose 1-D grid is partitioned into
+// four block ranges (u_phi cells | u_theta cells | density cells | particles). All four
+// read the pre-advection velocity, as in the reference.
+#include "kamino_kernels.cuh"
+#include "sampler.cuh"
+
+namespace kb {
+
+namespace {
+
+constexpr int kAdvectThreads = 256;
+
+// One RK2 backtrace from the node of `KIND` cell (j, i); samples `src` at the foot point.
+// kernel/KaminoCore.cu:195-228 (and :240-273, :285-318). Arithmetic notes:
+//  * node coordinate ((fReal)i + offset) * gridLen is an exact fp64 sum and product
+//    rounded once, which equals the fp32 product of the exact fp32 sum;
+//  * g - 0.5*delta (fp64 in the reference) is an exact product and a sum of two fp32
+//    values, i.e. fmaf(-0.5, delta, g);
+//  * 0.5 * (mu + gu) is an fp32 add followed by an exact halving;
+//  * g - aver*cof is one FFMA in the reference's SASS.
+template <int KIND>
+__device__ __forceinline__ float backtrace(const GridParams& g, const float* __restrict__ velPhi,
+                                           const float* __restrict__ velTheta,
+                                           const float* __restrict__ src, int i, int j)
+{
+    const float offPhi = (KIND == kVPhi) ? -0.5f : 0.0f;
+    const float offTheta = (KIND == kVTheta) ? 1.0f : 0.5f;
+    const float gPhi = __fmul_rn(__fadd_rn((float)i, offPhi), g.h);
+    const float gTheta = __fmul_rn(__fadd_rn((float)j, offTheta), g.h);
+
+    const float guPhi = sample<kVPhi>(g, velPhi, gPhi, gTheta);
+    const float guTheta = sample<kVTheta>(g, velTheta, gPhi, gTheta);
+
+    const float latRadius = __fmul_rn(g.radius, sinf(gTheta));
+    const float cofPhi = __fdiv_rn(g.dt, latRadius);
+    const float cofTheta = g.cofTheta;
+
+    const float deltaPhi = __fmul_rn(guPhi, cofPhi);
+    const float deltaTheta = __fmul_rn(guTheta, cofTheta);
+
+    const float midPhi = __fmaf_rn(-0.5f, deltaPhi, gPhi);
+    const float midTheta = __fmaf_rn(-0.5f, deltaTheta, gTheta);
+    const float muPhi = sample<kVPhi>(g, velPhi, midPhi, midTheta);
+    const float muTheta = sample<kVTheta>(g, velTheta, midPhi, midTheta);
+
+    const float averuPhi = __fmul_rn(0.5f, __fadd_rn(muPhi, guPhi));
+    const float averuTheta = __fmul_rn(0.5f, __fadd_rn(muTheta, guTheta));
+
+    const float pPhi = __fmaf_rn(-averuPhi, cofPhi, gPhi);
+    const float pTheta = __fmaf_rn(-averuTheta, cofTheta, gTheta);
+
+    return sample<KIND>(g, src, pPhi, pTheta);
+}
+
+// kernel/KaminoCore.cu:321-342
+__device__ __forceinline__ float2 pushParticle(const GridParams& g, const float* __restrict__ velPhi,
+                                               const float* __restrict__ velTheta, float2 pos)
+{
+    const float posPhi = pos.x, posTheta = pos.y;
+    const float uPhi = sample<kVPhi>(g, velPhi, posPhi, posTheta);
+    const float uTheta = sample<kVTheta>(g, velTheta, posPhi, posTheta);
+    const float latRadius = __fmul_rn(g.radius, sinf(posTheta));
+    const float cofPhi = __fdiv_rn(g.dt, latRadius);
+    float updatedTheta = __fmaf_rn(uTheta, g.cofTheta, posTheta);
+    float updatedPhi = posPhi;
+    if (latRadius > 1e-7f) updatedPhi = __fmaf_rn(uPhi, cofPhi, posPhi);
+    validateCoord(updatedPhi, updatedTheta);
+    return make_float2(updatedPhi, updatedTheta);
+}
+
+__global__ void __launch_bounds__(kAdvectThreads)
+advectKernel(GridParams g, AdvectArgs a)
+{
+    const int sim = blockIdx.y;
+    const float* velPhi = a.velPhi + (size_t)sim * g.cells;
+    const float* velTheta = a.velTheta + (size_t)sim * g.cells;
+    const int N = g.nPhi;
+    int block = blockIdx.x;
+
+    if (block < a.blocksPhi) {
+        const int cell = block * kAdvectThreads + threadIdx.x;
+        const int j = cell >> g.log2NPhi, i = cell & (N - 1);
+        a.velPhiOut[(size_t)sim * g.cells + cell] = backtrace<kVPhi>(g, velPhi, velTheta, velPhi, i, j);
+        return;
+    }
+    block -= a.blocksPhi;
+    if (block < a.blocksTheta) {
+        const int cell = block * kAdvectThreads + threadIdx.x;
+        const int j = cell >> g.log2NPhi, i = cell & (N - 1);
+        if (j < g.nTheta - 1)
+            a.velThetaOut[(size_t)sim * g.cells + cell] = backtrace<kVTheta>(g, velPhi, velTheta, velTheta, i, j);
+        return;
+    }
+    block -= a.blocksTheta;
+    if (block < a.blocksDensity) {
+        const int cell = block * kAdvectThreads + threadIdx.x;
+        const int j = cell >> g.log2NPhi, i = cell & (N - 1);
+        const float* density = a.density + (size_t)sim * g.cells;
+        a.densityOut[(size_t)sim * g.cells + cell] = backtrace<kCentered>(g, velPhi, velTheta, density, i, j);
+        return;
+    }
+    block -= a.blocksDensity;
+    {
+        const long k = (long)block * kAdvectThreads + threadIdx.x;
+        if (k < g.numParticles) {                       // the reference has no tail guard (:323)
+            const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
+            float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
+            out[k] = pushParticle(g, velPhi, velTheta, in[k]);
+        }
+    }
+}
+
+template <int KIND>
+__global__ void locateKernel(GridParams g, long n, const float* __restrict__ phiRaw,
+                             const float* __restrict__ thetaRaw, int* phiIndex, int* thetaIndex,
+                             float* alphaPhi, float* alphaTheta, float* phiOut, float* thetaOut, int* flags)
+{
+    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Location loc = locate<KIND>(g, phiRaw[k], thetaRaw[k]);
+    phiIndex[k] = loc.phiIndex;
+    thetaIndex[k] = loc.thetaIndex;
+    alphaPhi[k] = loc.alphaPhi;
+    alphaTheta[k] = loc.alphaTheta;
+    phiOut[k] = loc.phi;
+    thetaOut[k] = loc.theta;
+    flags[k] = (loc.flipped ? 1 : 0) | (poleBranch<KIND>(g, loc) ? 2 : 0);
+}
+
+} // namespace
+
+cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
+{
+    const int cellBlocks = (int)(g.cells / kAdvectThreads);
+    a.blocksPhi = cellBlocks;
+    a.blocksTheta = cellBlocks;
+    a.blocksDensity = a.density ? cellBlocks : 0;
+    const int blocksParticles = (a.particles && g.numParticles > 0)
+        ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
+    dim3 grid(a.blocksPhi + a.blocksTheta + a.blocksDensity + blocksParticles, batch);
+    advectKernel<<<grid, kAdvectThreads, 0, stream>>>(g, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phiRaw, const float* thetaRaw,
+                         int* phiIndex, int* thetaIndex, float* alphaPhi, float* alphaTheta,
+                         float* phiOut, float* thetaOut, int* flags, cudaStream_t stream)
+{
+    const int threads = 256;
+    const int blocks = (int)((n + threads - 1) / threads);
+    if (blocks == 0) return cudaSuccess;
+    switch (kind) {
+    case kVPhi:
+        locateKernel<kVPhi><<<blocks, threads, 0, stream>>>(g, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
+                                                            alphaPhi, alphaTheta, phiOut, thetaOut, flags);
+        break;
+    case kVTheta:
+        locateKernel<kVTheta><<<blocks, threads, 0, stream>>>(g, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
+                                                              alphaPhi, alphaTheta, phiOut, thetaOut, flags);
+        break;
+    default:
+        locateKernel<kCentered><<<blocks, threads, 0, stream>>>(g, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
+                                                                alphaPhi, alphaTheta, phiOut, thetaOut, flags);
+        break;
+    }
+    return cudaGetLastError();
+}
+
+} // namespace kb

@@ -1,0 +1,140 @@
+// Host-side initialisers of the drop-in boundary: the FBM "curl noise" initial velocity and
+// the rand()-driven particle lattice. They run once, on the CPU, exactly as in the reference
+// (KaminoSolver::initialize_velocity, kernel/KaminoInitializer.cu:3-134; KaminoParticles
+// constructor, kernel/KaminoParticles.cu:20-62) so that a simulation started through this
+// library begins from bit-identical fields. Compile with -ffp-contract=off: the reference's
+// host code is plain SSE2 arithmetic without fused multiply-adds.
+#include <cmath>
+#include <cstdlib>
+
+#include "../../include/kamino_b200.h"
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+
+// value noise lattice hash in [0, 1) (kernel/KaminoInitializer.cu:127-134)
+float latticeHash(double x, double y)
+{
+    const float dotProd = (float)(x * 12.9898 + y * 4.1414);
+    const float val = (float)std::sin((double)dotProd * 43758.5453);
+    return val - std::floor(val);
+}
+
+// (1.0 - t) * a + t * b with the reference's mixed types (kernel/KaminoInitializer.cu:104-107)
+float mixWide(float a, float b, float t)
+{
+    const float tb = t * b;
+    return (float)((1.0 - (double)t) * (double)a + (double)tb);
+}
+
+// bilinear value noise (kernel/KaminoInitializer.cu:109-125)
+float valueNoise(float x, float y)
+{
+    const float x0 = std::floor(x), fx = x - x0;
+    const float y0 = std::floor(y), fy = y - y0;
+    const float n00 = latticeHash(x0, y0);
+    const float n10 = latticeHash(x0 + 1, y0);
+    const float n01 = latticeHash(x0, y0 + 1);
+    const float n11 = latticeHash(x0 + 1, y0 + 1);
+    return mixWide(mixWide(n00, n10, fx), mixWide(n01, n11, fx), fy);
+}
+
+// four octaves, persistence 0.5, anisotropic base resolution (kernel/KaminoInitializer.cu:87-102)
+float fbm(float x, float y)
+{
+    const float resX = 0.15f, resY = 0.5f, persistence = 0.5f;
+    float total = 0.0f;
+    for (int octave = 0; octave < 4; ++octave) {
+        const float freq = (float)std::pow(2.0, (double)octave);
+        const float amp = (float)std::pow((double)persistence, (double)octave);
+        total += amp * valueNoise(x * freq / resX, y * freq / resY);
+    }
+    const float norm = 1 - persistence;
+    return norm * total / 2.0f;
+}
+
+} // namespace
+
+extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi, float* velTheta)
+{
+    if (nTheta < 2 || !velPhi || !velTheta) return KAMINO_ERR_INVALID;
+    const int nPhi = 2 * nTheta;
+    const float h = (float)(kTwoPi / (double)nPhi);           // the solver's gridLen, KaminoSolver.cu:14
+    const float gain = (float)(4096.0 / (double)nPhi);        // KaminoInitializer.cu:9
+    const float scale = radius * h;
+
+    // u_phi: theta-difference of the noise, averaged over the two phi sides of the face
+    // (KaminoInitializer.cu:11-55; the i = 0 column wraps to 2*pi - h/2)
+    for (int j = 0; j < nTheta; ++j) {
+        const float yUp = (float)(j + 1) * h, yLo = (float)j * h;
+        for (int i = 0; i < nPhi; ++i) {
+            const float xR = (i == 0) ? h / 2 : (float)i * h + h / 2;
+            const float xL = (i == 0) ? (float)(2 * kPi - (double)(h / 2)) : (float)i * h - h / 2;
+            const float dR = (fbm(xR, yUp) - fbm(xR, yLo)) / scale;
+            const float dL = (fbm(xL, yUp) - fbm(xL, yLo)) / scale;
+            velPhi[(size_t)j * nPhi + i] = (float)((double)(dR + dL) / 2.0) * gain;
+        }
+    }
+    // u_theta: minus the phi-difference; the reference's lower-left sample reuses the upper
+    // row (KaminoInitializer.cu:69), which is kept
+    for (int j = 1; j < nTheta; ++j) {
+        const float yUp = (float)j * h + h / 2, yLo = (float)j * h - h / 2;
+        for (int i = 0; i < nPhi; ++i) {
+            const float xR = (float)(i + 1) * h, xL = (float)i * h;
+            const float upperLeft = fbm(xL, yUp);
+            const float dU = -1.0f * (fbm(xR, yUp) - upperLeft) / scale;
+            const float dD = -1.0f * (fbm(xR, yLo) - upperLeft) / scale;
+            velTheta[(size_t)(j - 1) * nPhi + i] = (float)((double)(dU + dD) / 2.0) * gain;
+        }
+    }
+    return 0;
+}
+
+namespace {
+struct LatticeShape { float spacing; unsigned nTheta, nPhi; };
+
+LatticeShape latticeShape(int nTheta, float particleDensity)
+{
+    const float linear = std::sqrt(particleDensity);                       // KaminoParticles.cu:20
+    LatticeShape s;
+    s.spacing = (float)(kPi / (double)nTheta / (double)linear);           // :21
+    s.nTheta = (unsigned)(linear * (float)nTheta);                        // :24
+    s.nPhi = 2 * s.nTheta;                                                // :25
+    return s;
+}
+} // namespace
+
+extern "C" long kamino_particle_count(int nTheta, float particleDensity)
+{
+    if (nTheta < 1 || !(particleDensity >= 0.f)) return 0;
+    const LatticeShape s = latticeShape(nTheta, particleDensity);
+    return (long)s.nTheta * (long)s.nPhi;
+}
+
+extern "C" int kamino_seed_particles_host(int nTheta, float particleDensity, float* coords)
+{
+    if (nTheta < 1 || !(particleDensity >= 0.f) || !coords) return KAMINO_ERR_INVALID;
+    const LatticeShape s = latticeShape(nTheta, particleDensity);
+    const float half = (float)((double)s.spacing / 2.0);
+    const float randMax = (float)RAND_MAX;
+    std::srand(1);       // the reference never seeds: glibc starts in the srand(1) state
+    for (unsigned i = 0; i < s.nPhi; ++i) {
+        for (unsigned j = 0; j < s.nTheta; ++j) {
+            // four draws per particle in this order: sign phi, sign theta, jitter phi, jitter theta (:39-46)
+            const float sp = ((double)((float)std::rand() / randMax) >= 0.5) ? 1.0f : -1.0f;
+            const float st = ((double)((float)std::rand() / randMax) >= 0.5) ? 1.0f : -1.0f;
+            const float jitterPhi = sp * half * (float)std::rand() / randMax;
+            const float jitterTheta = st * half * (float)std::rand() / randMax;
+            float phi = (float)i * s.spacing + jitterPhi;
+            float theta = (float)j * s.spacing + jitterTheta;
+            if (phi < 0.0f) phi = 0.0f;
+            if (theta < 0.0f) theta = 0.0f;
+            const size_t at = (size_t)i * s.nTheta + j;
+            coords[2 * at] = phi;
+            coords[2 * at + 1] = theta;
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,49 @@
+// Shared device/host definitions for the kamino_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kb {
+
+// pi and 2*pi as the reference spells them (include/KaminoHeader.cuh:26-27): doubles.
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+// The fp32 neighbours of those constants from above. For an fp32 x:
+//   (double)x > kPi   <=>  x >= kPiF      (kPi lies strictly between two fp32 values)
+//   0 <= x < kTwoPiF   =>  floorf((float)((double)x / kTwoPi)) == 0
+// (see DESIGN.md "exactness notes").
+constexpr float kPiF = 3.14159274101257324f;      // 0x40490FDB
+constexpr float kTwoPiF = 6.28318548202514648f;   // 0x40C90FDB
+
+enum SampleKind { kVPhi = 0, kVTheta = 1, kCentered = 2 };
+
+// Per-context constants, passed to every kernel by value (lands in the constant bank).
+struct GridParams {
+    int nTheta;        // rows of u_phi / density / pressure; u_theta has nTheta - 1
+    int nPhi;          // 2 * nTheta, power of two
+    int log2NPhi;
+    float radius;      // radiusGlobal
+    float dt;          // timeStepGlobal
+    float h;           // gridLenGlobal = (float)(pi / nTheta)
+    float invH;        // (float)(1.0 / (double)h)   (kernel/KaminoCore.cu:42)
+    float halfH;       // 0.5f * h (exact)
+    float cofTheta;    // dt / radius                (kernel/KaminoCore.cu:204)
+    size_t cells;      // nTheta * nPhi : per-simulation stride of every field buffer
+    long numParticles; // per simulation
+};
+
+// Field buffers of the whole batch; simulation b starts at ptr + b * cells.
+struct FieldSet {
+    const float* velPhi;
+    const float* velTheta;
+    const float* density;
+};
+
+#define KB_CUDA_OK(expr)                                                     \
+    do {                                                                     \
+        cudaError_t kb_err__ = (expr);                                       \
+        if (kb_err__ != cudaSuccess) return (int)kb_err__;                   \
+    } while (0)
+
+} // namespace kb

@@ -1,0 +1,574 @@
+// Context, memory layout, step graphs and the C ABI of kamino_b200 (include/kamino_b200.h).
+//
+// HBM layout (one arena per context, every sub-buffer 256-byte aligned, batch-major):
+//   velPhi[2], velTheta[2], density[2]   batch x nTheta x nPhi fp32 each (u_theta uses
+//                                        nTheta-1 rows of its slot), double-buffered
+//   pressure                             batch x nTheta x nPhi fp32
+//   spectrum                             batch x nTheta x nPhi/2 float2 (half spectrum)
+//   particles[2]                         batch x numParticles float2, double-buffered
+//   tables                               twiddles + per-row constants
+// = 36 B/cell + 16 B/particle (the reference: 76 B/cell).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/kamino_b200.h"
+#include "kamino_kernels.cuh"
+
+using namespace kb;
+
+struct kamino_ctx {
+    int device = 0;
+    int batch = 1;
+    GridParams g{};
+    cudaStream_t ownStream = nullptr;    // graphs are captured here
+    cudaStream_t copyStream = nullptr;   // frame read-backs
+    cudaStream_t stream = nullptr;       // where work is launched (ownStream unless overridden)
+    char* arena = nullptr;          // fields, spectrum, tables
+    size_t arenaBytes = 0;
+    char* particleArena = nullptr;  // particles[2] + read-back snapshot (sized by kamino_alloc_particles)
+
+    float* velPhi[2]{};
+    float* velTheta[2]{};
+    float* density[2]{};
+    float* pressure = nullptr;
+    float2* spectrum = nullptr;
+    float* particles[2]{};
+    float* snapshot = nullptr;           // staging for overlapped frame read-backs
+    size_t snapshotFloats = 0;
+    SpectralTables tables{};
+
+    int velIdx = 0, densityIdx = 0, particleIdx = 0;   // which buffer is "this step"
+
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (parity, steps) -> exec
+
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evSnap = nullptr, evCopied = nullptr;
+    float advectionTime = 0.f, geometricTime = 0.f, projectionTime = 0.f;
+
+    std::string lastError;
+};
+
+namespace {
+
+thread_local std::string g_createError;
+
+int fail(kamino_ctx* ctx, int code, const std::string& what)
+{
+    std::string msg = what;
+    if (code > 0 && code < 10000) {
+        msg += ": ";
+        msg += cudaGetErrorString((cudaError_t)code);
+    }
+    if (ctx) ctx->lastError = msg; else g_createError = msg;
+    return code;
+}
+
+#define KB_TRY(ctx, expr)                                                        \
+    do {                                                                         \
+        cudaError_t kb_e__ = (expr);                                             \
+        if (kb_e__ != cudaSuccess) return fail((ctx), (int)kb_e__, #expr);       \
+    } while (0)
+
+struct DeviceGuard {
+    int previous = -1;
+    explicit DeviceGuard(int device) { cudaGetDevice(&previous); if (previous != device) cudaSetDevice(device); else previous = -1; }
+    ~DeviceGuard() { if (previous >= 0) cudaSetDevice(previous); }
+};
+
+size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t fieldRows(const kamino_ctx* ctx, int field)
+{
+    return field == KAMINO_VEL_THETA ? (size_t)ctx->g.nTheta - 1 : (size_t)ctx->g.nTheta;
+}
+
+float* fieldBuffer(kamino_ctx* ctx, int field, int which)
+{
+    switch (field) {
+    case KAMINO_VEL_PHI: return ctx->velPhi[ctx->velIdx ^ which];
+    case KAMINO_VEL_THETA: return ctx->velTheta[ctx->velIdx ^ which];
+    case KAMINO_DENSITY: return ctx->density[ctx->densityIdx ^ which];
+    case KAMINO_PRESSURE: return ctx->pressure;
+    default: return nullptr;
+    }
+}
+
+// enqueue the kernels of one phase on `s`, using and updating the index state `st`
+struct IndexState { int vel, density, particle; };
+
+cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
+{
+    AdvectArgs a{};
+    a.velPhi = ctx->velPhi[st.vel];
+    a.velTheta = ctx->velTheta[st.vel];
+    a.density = ctx->density[st.density];
+    a.particles = ctx->g.numParticles > 0 ? ctx->particles[st.particle] : nullptr;
+    a.velPhiOut = ctx->velPhi[st.vel ^ 1];
+    a.velThetaOut = ctx->velTheta[st.vel ^ 1];
+    a.densityOut = ctx->density[st.density ^ 1];
+    a.particlesOut = ctx->g.numParticles > 0 ? ctx->particles[st.particle ^ 1] : nullptr;
+    cudaError_t e = launchAdvect(ctx->g, a, ctx->batch, s);
+    st.vel ^= 1; st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
+    return e;
+}
+
+cudaError_t enqueueGeometric(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
+{
+    cudaError_t e = launchGeometric(ctx->g, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
+                                    ctx->velPhi[st.vel ^ 1], ctx->velTheta[st.vel ^ 1], ctx->batch, s);
+    st.vel ^= 1;                                          // kernel/KaminoCore.cu:582
+    return e;
+}
+
+cudaError_t enqueueProject(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
+{
+    cudaError_t e = launchDivergenceFFT(ctx->g, ctx->tables, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
+                                        ctx->spectrum, ctx->batch, s);
+    if (e != cudaSuccess) return e;
+    e = launchTridiagonal(ctx->g, ctx->tables, ctx->spectrum, ctx->batch, s);
+    if (e != cudaSuccess) return e;
+    // the velocity is corrected in place; the reference writes the "next" buffer and swaps
+    // (kernel/KaminoCore.cu:828-841), which is the same state for every caller of this ABI
+    return launchInverseFFTGradient(ctx->g, ctx->tables, ctx->spectrum, ctx->velPhi[st.vel],
+                                    ctx->velTheta[st.vel], ctx->pressure, ctx->batch, s);
+}
+
+cudaError_t enqueueStep(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
+{
+    cudaError_t e = enqueueAdvect(ctx, st, s);
+    if (e != cudaSuccess) return e;
+    e = enqueueGeometric(ctx, st, s);
+    if (e != cudaSuccess) return e;
+    return enqueueProject(ctx, st, s);
+}
+
+void dropGraphs(kamino_ctx* ctx)
+{
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+}
+
+// A graph of `steps` consecutive steps for the current buffer roles. The velocity index
+// returns to its starting value after every step; density and particles flip once per step.
+int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
+{
+    const int roles = (ctx->velIdx << 2) | (ctx->densityIdx << 1) | ctx->particleIdx;
+    auto key = std::make_pair(roles, steps);
+    auto it = ctx->graphs.find(key);
+    if (it != ctx->graphs.end()) { *out = it->second; return 0; }
+    IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
+    cudaGraph_t graph = nullptr;
+    KB_TRY(ctx, cudaStreamBeginCapture(ctx->ownStream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < steps && e == cudaSuccess; ++k) e = enqueueStep(ctx, st, ctx->ownStream);
+    cudaError_t e2 = cudaStreamEndCapture(ctx->ownStream, &graph);
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(ctx, (int)e, "graph capture (launch)"); }
+    if (e2 != cudaSuccess) return fail(ctx, (int)e2, "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "cudaGraphInstantiate");
+    ctx->graphs[key] = exec;
+    *out = exec;
+    return 0;
+}
+
+template <typename F>
+int timedPhase(kamino_ctx* ctx, float& accumulator, F&& enqueue)
+{
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
+    cudaError_t e = enqueue(st);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "kernel launch");
+    ctx->velIdx = st.vel; ctx->densityIdx = st.density; ctx->particleIdx = st.particle;
+    KB_TRY(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
+    KB_TRY(ctx, cudaEventSynchronize(ctx->evStop));
+    float ms = 0.f;
+    KB_TRY(ctx, cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop));
+    accumulator += ms * 0.001f;
+    return 0;
+}
+
+int checkSim(kamino_ctx* ctx, int sim)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (sim < 0 || sim >= ctx->batch) return fail(ctx, KAMINO_ERR_INVALID, "simulation index out of range");
+    return 0;
+}
+
+// (re)allocate the particle double buffer and the frame snapshot for n particles per simulation
+int allocParticles(kamino_ctx* ctx, long n)
+{
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dropGraphs(ctx);
+    if (ctx->particleArena) { cudaFree(ctx->particleArena); ctx->particleArena = nullptr; }
+    GridParams& g = ctx->g;
+    g.numParticles = n;
+    const size_t particleBytes = alignUp(sizeof(float) * 2 * (size_t)n * ctx->batch, 256);
+    ctx->snapshotFloats = (g.cells * 3 + 2 * (size_t)n) * ctx->batch;
+    const size_t snapshotBytes = alignUp(sizeof(float) * ctx->snapshotFloats, 256);
+    KB_TRY(ctx, cudaMalloc((void**)&ctx->particleArena, particleBytes * 2 + snapshotBytes));
+    KB_TRY(ctx, cudaMemset(ctx->particleArena, 0, particleBytes * 2 + snapshotBytes));
+    ctx->particles[0] = (float*)ctx->particleArena;
+    ctx->particles[1] = (float*)(ctx->particleArena + particleBytes);
+    ctx->snapshot = (float*)(ctx->particleArena + 2 * particleBytes);
+    ctx->particleIdx = ctx->densityIdx;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* kamino_version(void) { return "kamino_b200 0.1 sm_100a"; }
+
+const char* kamino_last_error(const kamino_ctx* ctx)
+{
+    return ctx ? ctx->lastError.c_str() : g_createError.c_str();
+}
+
+int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float dt, int batch, long particlesPerSim)
+{
+    if (!out) return fail(nullptr, KAMINO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (nTheta < 16 || (nTheta & (nTheta - 1)) != 0 || nTheta > 8192)
+        return fail(nullptr, KAMINO_ERR_INVALID, "nTheta must be a power of two in [16, 8192]");
+    if (batch < 1 || particlesPerSim < 0 || !(radius > 0.f) || !(dt > 0.f))
+        return fail(nullptr, KAMINO_ERR_INVALID, "batch >= 1, particles >= 0, radius > 0, dt > 0 required");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, KAMINO_ERR_NO_DEVICE, "no CUDA device available (kamino_b200 has no CPU path)");
+    if (device < 0 || device >= count) return fail(nullptr, KAMINO_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    KB_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, KAMINO_ERR_NO_DEVICE, "kamino_b200 is built for sm_100a (B200) only");
+
+    DeviceGuard guard(device);
+    kamino_ctx* ctx = new kamino_ctx();
+    ctx->device = device;
+    ctx->batch = batch;
+    GridParams& g = ctx->g;
+    g.nTheta = nTheta;
+    g.nPhi = 2 * nTheta;
+    g.log2NPhi = 0;
+    while ((1 << g.log2NPhi) < g.nPhi) ++g.log2NPhi;
+    g.radius = radius;
+    g.dt = dt;
+    g.h = (float)(kPi / (double)nTheta);                  // kernel/KaminoCore.cu:849
+    g.invH = (float)(1.0 / (double)g.h);
+    g.halfH = 0.5f * g.h;
+    g.cofTheta = dt / radius;
+    g.cells = (size_t)g.nTheta * g.nPhi;
+    g.numParticles = particlesPerSim;
+
+    const size_t fieldBytes = alignUp(sizeof(float) * g.cells * batch, 256);
+    const size_t tableBytes = alignUp(spectralTableBytes(g), 256);
+    ctx->arenaBytes = fieldBytes * 8 + tableBytes;
+    e = cudaMalloc((void**)&ctx->arena, ctx->arenaBytes);
+    if (e != cudaSuccess) { int rc = fail(nullptr, (int)e, "cudaMalloc(arena)"); delete ctx; return rc; }
+    cudaMemset(ctx->arena, 0, ctx->arenaBytes);
+    char* p = ctx->arena;
+    auto take = [&p](size_t bytes) { char* r = p; p += bytes; return r; };
+    for (int k = 0; k < 2; ++k) ctx->velPhi[k] = (float*)take(fieldBytes);
+    for (int k = 0; k < 2; ++k) ctx->velTheta[k] = (float*)take(fieldBytes);
+    for (int k = 0; k < 2; ++k) ctx->density[k] = (float*)take(fieldBytes);
+    ctx->pressure = (float*)take(fieldBytes);
+    ctx->spectrum = (float2*)take(fieldBytes);
+    {
+        char* t = take(tableBytes);
+        auto sub = [&t](size_t bytes) { char* r = t; t += alignUp(bytes, 256); return r; };
+        ctx->tables.twiddle = (float2*)sub(sizeof(float2) * g.nPhi);
+        ctx->tables.divFactor = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.sinNorth = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.sinSouth = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.gradPhiDenom = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.triA = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.triC = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.sinSq = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.minusTwoOverH2 = -2.0 / (double)(g.h * g.h);
+    }
+
+    bool ok = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) == cudaSuccess
+        && cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) == cudaSuccess
+        && cudaEventCreate(&ctx->evStart) == cudaSuccess && cudaEventCreate(&ctx->evStop) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->evSnap, cudaEventDisableTiming) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming) == cudaSuccess;
+    ctx->stream = ctx->ownStream;
+    if (ok) ok = configureKernels(g) == cudaSuccess;
+    if (ok) ok = launchBuildTables(g, ctx->tables, ctx->stream) == cudaSuccess;
+    if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (ok) ok = allocParticles(ctx, particlesPerSim) == 0;
+    if (!ok) {
+        int rc = fail(nullptr, (int)cudaGetLastError(), "context setup");
+        if (rc == 0) rc = fail(nullptr, KAMINO_ERR_STATE, "context setup failed");
+        kamino_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+int kamino_destroy(kamino_ctx* ctx)
+{
+    if (!ctx) return 0;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dropGraphs(ctx);
+    if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+    if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+    if (ctx->evSnap) cudaEventDestroy(ctx->evSnap);
+    if (ctx->evCopied) cudaEventDestroy(ctx->evCopied);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->particleArena) cudaFree(ctx->particleArena);
+    delete ctx;
+    return 0;
+}
+
+int kamino_alloc_particles(kamino_ctx* ctx, long particlesPerSim)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (particlesPerSim < 0) return fail(ctx, KAMINO_ERR_INVALID, "particlesPerSim < 0");
+    return allocParticles(ctx, particlesPerSim);
+}
+
+int kamino_set_stream(kamino_ctx* ctx, void* cudaStream)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cudaStream ? (cudaStream_t)cudaStream : ctx->ownStream;
+    return 0;
+}
+
+int kamino_get_shape(const kamino_ctx* ctx, int* nTheta, int* nPhi, int* batch, long* particlesPerSim)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (nTheta) *nTheta = ctx->g.nTheta;
+    if (nPhi) *nPhi = ctx->g.nPhi;
+    if (batch) *batch = ctx->batch;
+    if (particlesPerSim) *particlesPerSim = ctx->g.numParticles;
+    return 0;
+}
+
+static int copyField(kamino_ctx* ctx, int field, int sim, void* host, bool toDevice, bool async)
+{
+    if (int rc = checkSim(ctx, sim)) return rc;
+    if (!host) return fail(ctx, KAMINO_ERR_INVALID, "host pointer is NULL");
+    float* base = fieldBuffer(ctx, field, 0);
+    if (!base) return fail(ctx, KAMINO_ERR_INVALID, "unknown field");
+    DeviceGuard guard(ctx->device);
+    float* dev = base + (size_t)sim * ctx->g.cells;
+    const size_t bytes = sizeof(float) * fieldRows(ctx, field) * ctx->g.nPhi;
+    if (toDevice) KB_TRY(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else KB_TRY(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!async) KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int copyParticles(kamino_ctx* ctx, int sim, void* host, bool toDevice, bool async)
+{
+    if (int rc = checkSim(ctx, sim)) return rc;
+    if (ctx->g.numParticles == 0) return 0;     // kernel/KaminoParticles.cu:96,105
+    if (!host) return fail(ctx, KAMINO_ERR_INVALID, "host pointer is NULL");
+    DeviceGuard guard(ctx->device);
+    float* dev = ctx->particles[ctx->particleIdx] + (size_t)sim * 2 * ctx->g.numParticles;
+    const size_t bytes = sizeof(float) * 2 * (size_t)ctx->g.numParticles;
+    if (toDevice) KB_TRY(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else KB_TRY(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!async) KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int kamino_upload_field(kamino_ctx* ctx, int field, int sim, const float* host)
+{ return copyField(ctx, field, sim, (void*)host, true, false); }
+int kamino_download_field(kamino_ctx* ctx, int field, int sim, float* host)
+{ return copyField(ctx, field, sim, host, false, false); }
+int kamino_upload_particles(kamino_ctx* ctx, int sim, const float* host)
+{ return copyParticles(ctx, sim, (void*)host, true, false); }
+int kamino_download_particles(kamino_ctx* ctx, int sim, float* host)
+{ return copyParticles(ctx, sim, host, false, false); }
+int kamino_download_field_async(kamino_ctx* ctx, int field, int sim, float* host)
+{ return copyField(ctx, field, sim, host, false, true); }
+int kamino_download_particles_async(kamino_ctx* ctx, int sim, float* host)
+{ return copyParticles(ctx, sim, host, false, true); }
+int kamino_upload_field_async(kamino_ctx* ctx, int field, int sim, const float* host)
+{ return copyField(ctx, field, sim, (void*)host, true, true); }
+int kamino_upload_particles_async(kamino_ctx* ctx, int sim, const float* host)
+{ return copyParticles(ctx, sim, (void*)host, true, true); }
+
+int kamino_field_device_ptr(kamino_ctx* ctx, int field, int sim, int which, void** devicePtr, size_t* pitchInElements)
+{
+    if (int rc = checkSim(ctx, sim)) return rc;
+    float* base = fieldBuffer(ctx, field, which ? 1 : 0);
+    if (!base || !devicePtr) return fail(ctx, KAMINO_ERR_INVALID, "unknown field or NULL output");
+    *devicePtr = base + (size_t)sim * ctx->g.cells;
+    if (pitchInElements) *pitchInElements = (size_t)ctx->g.nPhi;
+    return 0;
+}
+
+int kamino_particles_device_ptr(kamino_ctx* ctx, int sim, int which, void** devicePtr)
+{
+    if (int rc = checkSim(ctx, sim)) return rc;
+    if (!devicePtr) return fail(ctx, KAMINO_ERR_INVALID, "NULL output");
+    *devicePtr = ctx->particles[ctx->particleIdx ^ (which ? 1 : 0)] + (size_t)sim * 2 * ctx->g.numParticles;
+    return 0;
+}
+
+int kamino_advect(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    return timedPhase(ctx, ctx->advectionTime, [&](IndexState& st) { return enqueueAdvect(ctx, st, ctx->stream); });
+}
+
+int kamino_geometric(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    return timedPhase(ctx, ctx->geometricTime, [&](IndexState& st) { return enqueueGeometric(ctx, st, ctx->stream); });
+}
+
+int kamino_project(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    return timedPhase(ctx, ctx->projectionTime, [&](IndexState& st) { return enqueueProject(ctx, st, ctx->stream); });
+}
+
+int kamino_step(kamino_ctx* ctx, int nSteps)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (nSteps < 0) return fail(ctx, KAMINO_ERR_INVALID, "nSteps < 0");
+    DeviceGuard guard(ctx->device);
+    static const int chunks[] = {10, 2, 1};
+    int remaining = nSteps;
+    while (remaining > 0) {
+        int take = 1;
+        for (int c : chunks)
+            if (c <= remaining) { take = c; break; }
+        cudaGraphExec_t exec = nullptr;
+        if (int rc = getGraph(ctx, take, &exec)) return rc;
+        KB_TRY(ctx, cudaGraphLaunch(exec, ctx->stream));
+        if (take & 1) { ctx->densityIdx ^= 1; ctx->particleIdx ^= 1; }
+        remaining -= take;
+    }
+    return 0;
+}
+
+int kamino_sync(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->copyStream));
+    return 0;
+}
+
+int kamino_run_frames(kamino_ctx* ctx, int nFrames, int stepsPerFrame, float* hostVelPhi, float* hostVelTheta,
+                      float* hostDensity, float* hostParticles)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (nFrames < 0 || stepsPerFrame < 1) return fail(ctx, KAMINO_ERR_INVALID, "nFrames >= 0, stepsPerFrame >= 1 required");
+    DeviceGuard guard(ctx->device);
+    const GridParams& g = ctx->g;
+    const size_t fieldFloats = g.cells * ctx->batch;
+    const size_t particleFloats = 2 * (size_t)g.numParticles * ctx->batch;
+    float* snapPhi = ctx->snapshot;
+    float* snapTheta = snapPhi + fieldFloats;
+    float* snapRho = snapTheta + fieldFloats;
+    float* snapPart = snapRho + fieldFloats;
+    for (int f = 0; f < nFrames; ++f) {
+        if (int rc = kamino_step(ctx, stepsPerFrame)) return rc;
+        // device-side snapshot so that the read-back of frame f overlaps the steps of frame f+1
+        KB_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopied, 0));
+        if (hostVelPhi) KB_TRY(ctx, cudaMemcpyAsync(snapPhi, ctx->velPhi[ctx->velIdx], sizeof(float) * fieldFloats, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (hostVelTheta) KB_TRY(ctx, cudaMemcpyAsync(snapTheta, ctx->velTheta[ctx->velIdx], sizeof(float) * fieldFloats, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (hostDensity) KB_TRY(ctx, cudaMemcpyAsync(snapRho, ctx->density[ctx->densityIdx], sizeof(float) * fieldFloats, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (hostParticles && particleFloats) KB_TRY(ctx, cudaMemcpyAsync(snapPart, ctx->particles[ctx->particleIdx], sizeof(float) * particleFloats, cudaMemcpyDeviceToDevice, ctx->stream));
+        KB_TRY(ctx, cudaEventRecord(ctx->evSnap, ctx->stream));
+        KB_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evSnap, 0));
+        // host layout: simulation-major, each field dense (u_theta keeps nTheta-1 rows per simulation)
+        if (hostVelPhi) KB_TRY(ctx, cudaMemcpyAsync(hostVelPhi, snapPhi, sizeof(float) * fieldFloats, cudaMemcpyDeviceToHost, ctx->copyStream));
+        if (hostVelTheta)
+            KB_TRY(ctx, cudaMemcpy2DAsync(hostVelTheta, sizeof(float) * (g.cells - g.nPhi), snapTheta, sizeof(float) * g.cells,
+                                          sizeof(float) * (g.cells - g.nPhi), ctx->batch, cudaMemcpyDeviceToHost, ctx->copyStream));
+        if (hostDensity) KB_TRY(ctx, cudaMemcpyAsync(hostDensity, snapRho, sizeof(float) * fieldFloats, cudaMemcpyDeviceToHost, ctx->copyStream));
+        if (hostParticles && particleFloats) KB_TRY(ctx, cudaMemcpyAsync(hostParticles, snapPart, sizeof(float) * particleFloats, cudaMemcpyDeviceToHost, ctx->copyStream));
+        KB_TRY(ctx, cudaEventRecord(ctx->evCopied, ctx->copyStream));
+    }
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->copyStream));
+    return 0;
+}
+
+int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, float* projection, int reset)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (advection) *advection = ctx->advectionTime;
+    if (geometric) *geometric = ctx->geometricTime;
+    if (projection) *projection = ctx->projectionTime;
+    if (reset) ctx->advectionTime = ctx->geometricTime = ctx->projectionTime = 0.f;
+    return 0;
+}
+
+int kamino_launches_per_step(const kamino_ctx*) { return 5; }
+
+int kamino_debug_locate(kamino_ctx* ctx, int kind, long n, const float* phiRaw, const float* thetaRaw,
+                        int32_t* phiIndex, int32_t* thetaIndex, float* alphaPhi, float* alphaTheta,
+                        float* phiValidated, float* thetaValidated, int32_t* flags)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (kind < 0 || kind > 2 || n < 0) return fail(ctx, KAMINO_ERR_INVALID, "bad kind or n");
+    if (n == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    char* scratch = nullptr;
+    const size_t one = alignUp(sizeof(float) * (size_t)n, 256);
+    KB_TRY(ctx, cudaMalloc((void**)&scratch, one * 9));
+    float* dPhi = (float*)scratch;
+    float* dTheta = (float*)(scratch + one);
+    int* dPi = (int*)(scratch + 2 * one);
+    int* dTi = (int*)(scratch + 3 * one);
+    float* dAp = (float*)(scratch + 4 * one);
+    float* dAt = (float*)(scratch + 5 * one);
+    float* dPv = (float*)(scratch + 6 * one);
+    float* dTv = (float*)(scratch + 7 * one);
+    int* dFl = (int*)(scratch + 8 * one);
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaMemcpyAsync(dPhi, phiRaw, sizeof(float) * n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dTheta, thetaRaw, sizeof(float) * n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launchLocate(ctx->g, kind, n, dPhi, dTheta, dPi, dTi, dAp, dAt, dPv, dTv, dFl, s);
+    auto back = [&](void* host, const void* dev) {
+        if (e == cudaSuccess && host) e = cudaMemcpyAsync(host, dev, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
+    };
+    back(phiIndex, dPi); back(thetaIndex, dTi); back(alphaPhi, dAp); back(alphaTheta, dAt);
+    back(phiValidated, dPv); back(thetaValidated, dTv); back(flags, dFl);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "kamino_debug_locate");
+    return 0;
+}
+
+int kamino_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail(nullptr, KAMINO_ERR_INVALID, "ptr is NULL");
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) return fail(nullptr, (int)e, "cudaMallocHost");
+    return 0;
+}
+
+int kamino_host_free(void* ptr)
+{
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return fail(nullptr, (int)e, "cudaFreeHost");
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,62 @@
+// Launch interfaces of the kamino_b200 kernels. One step = five launches:
+//   advect -> geometric -> divergence+forward FFT -> tridiagonal -> inverse FFT+gradient
+#pragma once
+
+#include "kamino_common.cuh"
+
+namespace kb {
+
+struct AdvectArgs {
+    const float* velPhi;       // this-step buffers (whole batch)
+    const float* velTheta;
+    const float* density;      // may be NULL
+    const float* particles;    // may be NULL; interleaved (phi, theta)
+    float* velPhiOut;          // next-step buffers
+    float* velThetaOut;
+    float* densityOut;
+    float* particlesOut;
+    int blocksPhi, blocksTheta, blocksDensity;   // filled by launchAdvect
+};
+
+cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
+
+cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phiRaw, const float* thetaRaw,
+                         int* phiIndex, int* thetaIndex, float* alphaPhi, float* alphaTheta,
+                         float* phiOut, float* thetaOut, int* flags, cudaStream_t stream);
+
+// geometric phase: velPhi/velTheta (this) -> velPhiOut/velThetaOut (next)
+cudaError_t launchGeometric(const GridParams& g, const float* velPhi, const float* velTheta,
+                            float* velPhiOut, float* velThetaOut, int batch, cudaStream_t stream);
+
+// Per-context read-only tables for the projection (built once by launchBuildTables).
+struct SpectralTables {
+    float2* twiddle;      // nPhi entries: exp(-2 pi i k / nPhi)
+    float* divFactor;     // nTheta: invGridSine / gridLen        (kernel/KaminoCore.cu:625,628)
+    float* sinNorth;      // nTheta: sinf(theta_j - h/2)          (:626)
+    float* sinSouth;      // nTheta: sinf(theta_j + h/2)          (:627)
+    float* gradPhiDenom;  // nTheta: -gridLen * sinf(theta_j)     (:743-744)
+    float* triA;          // nTheta: sub-diagonal before the Neumann fold (KaminoSolver.cu:135-136)
+    float* triC;          // nTheta: super-diagonal               (:137-138)
+    float* sinSq;         // nTheta: sinf(theta_j)^2              (:134)
+    double minusTwoOverH2;  // -2.0 / (h*h)                        (:133)
+};
+
+size_t spectralTableBytes(const GridParams& g);
+cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream);
+
+// spectrum layout: S[sim][j][k], k = 0 .. nPhi/2-1, float2; slot k holds wavenumber
+// n = k for k >= 1 and the Nyquist mode n = nPhi/2 in slot 0 (the n = 0 mode is never
+// projected by the reference, kernel/KaminoSolver.cu:154-159 + KaminoCore.cu:692-700).
+cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, const float* velPhi,
+                                const float* velTheta, float2* spectrum, int batch, cudaStream_t stream);
+cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
+                              cudaStream_t stream);
+// velPhi / velTheta updated in place; pressure (may be NULL) receives p.
+cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
+                                     float* velPhi, float* velTheta, float* pressure, int batch,
+                                     cudaStream_t stream);
+
+// One-time setup of kernel attributes (opt-in shared memory); called at context creation.
+cudaError_t configureKernels(const GridParams& g);
+
+} // namespace kb
