@@ -149,6 +149,13 @@ int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, floa
 /* Number of kernel launches one kamino_step(ctx, 1) performs (for bench.py's gpu_launches). */
 int kamino_launches_per_step(const kamino_ctx* ctx);
 
+/* Run nSteps steps with every kernel launched individually and bracketed by CUDA events on
+ * the context's stream; kernelSeconds[k] (k = 0 .. kamino_launches_per_step()-1: advection,
+ * geometric, divergence+FFT, tridiagonal, inverse FFT+gradient) receives the summed device
+ * time of kernel k. The per-kernel counterpart of the reference's per-phase KaminoTimer
+ * brackets (kernel/KaminoSolver.cu:201-218). Synchronous. */
+int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds);
+
 /* ---- host-side initialisers (pure CPU; reproduce the reference's initial state) ------ */
 
 /* KaminoSolver::initialize_velocity (kernel/KaminoInitializer.cu:3-134): FBM curl-noise

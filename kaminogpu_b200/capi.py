@@ -49,6 +49,7 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "kamino_phase_times": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int]),
     "kamino_launches_per_step": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_profile_steps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p]),
     "kamino_init_velocity_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "kamino_particle_count": (ctypes.c_long, [ctypes.c_int, ctypes.c_float]),
     "kamino_seed_particles_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_void_p]),

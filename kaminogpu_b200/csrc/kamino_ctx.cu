@@ -55,6 +55,8 @@ struct kamino_ctx {
 
 namespace {
 
+constexpr int kStepKernels = 5;
+
 thread_local std::string g_createError;
 
 int fail(kamino_ctx* ctx, int code, const std::string& what)
@@ -125,17 +127,38 @@ cudaError_t enqueueGeometric(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
     return e;
 }
 
+// the three kernels of the projection (part = 0, 1, 2)
+cudaError_t enqueueProjectPart(kamino_ctx* ctx, IndexState& st, int part, cudaStream_t s)
+{
+    switch (part) {
+    case 0:
+        return launchDivergenceFFT(ctx->g, ctx->tables, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
+                                   ctx->spectrum, ctx->batch, s);
+    case 1:
+        return launchTridiagonal(ctx->g, ctx->tables, ctx->spectrum, ctx->batch, s);
+    default:
+        // the velocity is corrected in place; the reference writes the "next" buffer and swaps
+        // (kernel/KaminoCore.cu:828-841), which is the same state for every caller of this ABI
+        return launchInverseFFTGradient(ctx->g, ctx->tables, ctx->spectrum, ctx->velPhi[st.vel],
+                                        ctx->velTheta[st.vel], ctx->pressure, ctx->batch, s);
+    }
+}
+
 cudaError_t enqueueProject(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
-    cudaError_t e = launchDivergenceFFT(ctx->g, ctx->tables, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
-                                        ctx->spectrum, ctx->batch, s);
-    if (e != cudaSuccess) return e;
-    e = launchTridiagonal(ctx->g, ctx->tables, ctx->spectrum, ctx->batch, s);
-    if (e != cudaSuccess) return e;
-    // the velocity is corrected in place; the reference writes the "next" buffer and swaps
-    // (kernel/KaminoCore.cu:828-841), which is the same state for every caller of this ABI
-    return launchInverseFFTGradient(ctx->g, ctx->tables, ctx->spectrum, ctx->velPhi[st.vel],
-                                    ctx->velTheta[st.vel], ctx->pressure, ctx->batch, s);
+    for (int part = 0; part < 3; ++part) {
+        cudaError_t e = enqueueProjectPart(ctx, st, part, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// kernel k of a step: 0 advect, 1 geometric, 2 divergence+FFT, 3 tridiagonal, 4 inverse FFT+gradient
+cudaError_t enqueueStepKernel(kamino_ctx* ctx, IndexState& st, int k, cudaStream_t s)
+{
+    if (k == 0) return enqueueAdvect(ctx, st, s);
+    if (k == 1) return enqueueGeometric(ctx, st, s);
+    return enqueueProjectPart(ctx, st, k - 2, s);
 }
 
 cudaError_t enqueueStep(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
@@ -519,7 +542,42 @@ int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, floa
     return 0;
 }
 
-int kamino_launches_per_step(const kamino_ctx*) { return 5; }
+int kamino_launches_per_step(const kamino_ctx*) { return kStepKernels; }
+
+int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (nSteps < 1 || !kernelSeconds) return fail(ctx, KAMINO_ERR_INVALID, "nSteps >= 1 and an output array required");
+    DeviceGuard guard(ctx->device);
+    std::vector<cudaEvent_t> ev((size_t)nSteps * (kStepKernels + 1));
+    for (auto& e : ev) KB_TRY(ctx, cudaEventCreate(&e));
+    IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
+    cudaError_t err = cudaSuccess;
+    for (int s = 0; s < nSteps && err == cudaSuccess; ++s) {
+        cudaEvent_t* e = &ev[(size_t)s * (kStepKernels + 1)];
+        err = cudaEventRecord(e[0], ctx->stream);
+        for (int k = 0; k < kStepKernels && err == cudaSuccess; ++k) {
+            err = enqueueStepKernel(ctx, st, k, ctx->stream);
+            if (err == cudaSuccess) err = cudaEventRecord(e[k + 1], ctx->stream);
+        }
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    ctx->velIdx = st.vel; ctx->densityIdx = st.density; ctx->particleIdx = st.particle;
+    double total[kStepKernels] = {};
+    for (int s = 0; s < nSteps && err == cudaSuccess; ++s) {
+        cudaEvent_t* e = &ev[(size_t)s * (kStepKernels + 1)];
+        for (int k = 0; k < kStepKernels; ++k) {
+            float ms = 0.f;
+            err = cudaEventElapsedTime(&ms, e[k], e[k + 1]);
+            if (err != cudaSuccess) break;
+            total[k] += ms * 1e-3;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (err != cudaSuccess) return fail(ctx, (int)err, "kamino_profile_steps");
+    for (int k = 0; k < kStepKernels; ++k) kernelSeconds[k] = (float)total[k];
+    return 0;
+}
 
 int kamino_debug_locate(kamino_ctx* ctx, int kind, long n, const float* phiRaw, const float* thetaRaw,
                         int32_t* phiIndex, int32_t* thetaIndex, float* alphaPhi, float* alphaTheta,

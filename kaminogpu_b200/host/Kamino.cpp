@@ -1,0 +1,52 @@
+#include "Kamino.h"
+
+#include "KaminoTimer.h"
+
+Kamino::Kamino(fReal radius, size_t nTheta, fReal particleDensity,
+    float dt, float DT, int frames,
+    fReal A, int B, int C, int D, int E,
+    std::string gridPath, std::string particlePath,
+    std::string densityImage, std::string solidImage, std::string colorImage) :
+    nTheta(nTheta), nPhi(2 * nTheta), gridLen((fReal)(M_PI / nTheta)), radius(radius),
+    dt(dt), DT(DT), frames(frames), particleDensity(particleDensity),
+    gridPath(gridPath), particlePath(particlePath),
+    densityImage(densityImage), solidImage(solidImage), colorImage(colorImage),
+    A(A), B(B), C(C), D(D), E(E)
+{}
+
+Kamino::~Kamino() {}
+
+// kernel/KaminoCore.cu:860-912. Steps per frame = (iterations of the while loop) + 1: the
+// "remainder" step is a full-dt step because the kernels ignore stepForward's argument.
+void Kamino::run()
+{
+    KaminoSolver solver(nPhi, nTheta, radius, dt, A, B, C, D, E);
+    solver.initDensityfromPic(densityImage);
+    solver.initParticlesfromPic(colorImage, (size_t)this->particleDensity);
+
+    const bool writeGrid = !(gridPath.empty() || gridPath == "null");
+    const bool writeParticles = !(particlePath.empty() || particlePath == "null");
+    if (writeGrid) solver.write_data_bgeo(gridPath, 0);
+    if (writeParticles) solver.write_particles_bgeo(particlePath, 0);
+
+    KaminoTimer timer(solver.context());
+    timer.startTimer();
+
+    float T = 0.0;
+    for (int i = 1; i <= frames; i++) {
+        while (T < i * DT) {
+            solver.stepForward(dt);
+            T += dt;
+        }
+        solver.stepForward(dt + i * DT - T);
+        T = i * DT;
+
+        std::cout << "Frame " << i << " is ready" << std::endl;
+        if (writeGrid) solver.write_data_bgeo(gridPath, i);
+        if (writeParticles) solver.write_particles_bgeo(particlePath, i);
+    }
+
+    float gpu_time = timer.stopTimer();
+    std::cout << "Time spent: " << gpu_time << "ms" << std::endl;
+    std::cout << "Performance: " << 1000.0 * frames / gpu_time << " frames per second" << std::endl;
+}

@@ -247,3 +247,20 @@ def load_config(path):
         if cfg[key] == "null":
             cfg[key] = ""
     return cfg
+
+
+def steps_per_frame(dt, DT, frames):
+    """Number of stepForward calls Kamino::run makes for each frame (kernel/KaminoCore.cu:886-895):
+    float arithmetic, the `while (T < i*DT)` iterations plus the always-taken remainder step."""
+    dt, DT = np.float32(dt), np.float32(DT)
+    T = np.float32(0.0)
+    out = []
+    for i in range(1, frames + 1):
+        n = 0
+        while T < np.float32(i) * DT:
+            T = np.float32(T + dt)
+            n += 1
+        n += 1
+        T = np.float32(i) * DT
+        out.append(n)
+    return out

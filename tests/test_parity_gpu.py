@@ -1,0 +1,476 @@
+"""GPU suite: the CUDA path (through the C ABI / the KaminoSolver mirror) against
+  (1) the committed dumps of the reference's own CUDA build (tests/golden/ref_*.npz),
+  (2) the CPU oracle on the same seeded inputs,
+  (3) size-independent properties at the BASELINE.json sizes.
+
+Tolerances (fp32 relative L2 per field, north star: <= 1e-5 per field per step):
+  advection, geometric, particles: 1e-5 asserted; these phases reproduce the reference's
+      arithmetic operation for operation and are expected bit-identical on the goldens
+      (asserted as >= 99.9% identical words so that a single double-rounding tie cannot
+      fail the suite; the exact fraction is printed).
+  projection: u_theta and pressure 1e-5. u_phi: 1e-5 away from the two rows next to each
+      pole; in those rows the phi gradient divides the fp32 round-off of p by
+      h*sin(theta) (3e-4 at nTheta=128), so two correct fp32 evaluations of the same operator
+      (cuFFT + transposes vs our FFT) differ by ~1e-3 there. The bound used for the whole
+      field is "no worse than 3x the reference's own distance from an fp64 evaluation"
+      (see DESIGN.md "projection parity").
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["t16", "t32", "t64", "t128"]
+
+
+@pytest.fixture(scope="module")
+def K(built):
+    from kaminogpu_b200 import capi, solver
+    capi.load()
+    return solver
+
+
+def words_equal(a, b):
+    a = np.ascontiguousarray(a, np.float32).ravel()
+    b = np.ascontiguousarray(b, np.float32).ravel()
+    return float((a.view(np.uint32) == b.view(np.uint32)).mean())
+
+
+def make_solver(K, g, particles=True, **kw):
+    nT = int(g["meta.nTheta"])
+    N = 2 * nT
+    s = K.KaminoSolver(N, nT, float(g["meta.radius"]), float(g["meta.dt"]), **kw)
+    s.density.cpuBuffer[:] = g["init.density"].reshape(nT, N)
+    s.density.copyToGPU()
+    if particles:
+        s.initParticlesfromPic("", 0, coords=g["init.particles"])
+    return s
+
+
+def set_velocity(s, u, v):
+    s.velPhi.cpuBuffer[:] = np.asarray(u).reshape(s.nTheta, s.nPhi)
+    s.velPhi.copyToGPU()
+    s.velTheta.cpuBuffer[:] = np.asarray(v).reshape(s.nTheta - 1, s.nPhi)
+    s.velTheta.copyToGPU()
+
+
+def state(s):
+    out = {"velPhi": s.velPhi.copyBackToCPU().ravel().copy(), "velTheta": s.velTheta.copyBackToCPU().ravel().copy(),
+           "density": s.density.copyBackToCPU().ravel().copy()}
+    if s.particles is not None:
+        out["particles"] = s.particles.copyBack2CPU().copy()
+    return out
+
+
+def fp64_projection(nT, u, v, radius=5.0, dt=0.005):
+    """fp64 evaluation of the reference's projection operator (rfft -> per-wavenumber
+    tridiagonal solve with the fp32 coefficient tables -> irfft, n = 0 dropped)."""
+    N = 2 * nT
+    p = oa.params(nT, radius, dt)
+    div = np.zeros(nT * N, np.float32)
+    oa.lib().ko_divergence(ctypes.byref(p), oa.fptr(np.ascontiguousarray(u)), oa.fptr(np.ascontiguousarray(v)), oa.fptr(div))
+    F = np.fft.rfft(div.reshape(nT, N).astype(np.float64), axis=1) / N
+    U = np.zeros_like(F)
+    from scipy.linalg import solve_banded
+    for n in range(1, N // 2 + 1):
+        a = np.zeros(nT, np.float32); b = np.zeros(nT, np.float32); c = np.zeros(nT, np.float32)
+        oa.lib().ko_abc_row(ctypes.byref(p), n, oa.fptr(a), oa.fptr(b), oa.fptr(c))
+        ab = np.zeros((3, nT))
+        ab[0, 1:] = c[:-1]; ab[1] = b; ab[2, :-1] = a[1:]
+        U[:, n] = solve_banded((1, 1), ab, F[:, n])
+    pr = np.fft.irfft(U * N, n=N, axis=1)
+    h = float(p.gridLen)
+    theta = (np.arange(nT) + 0.5) * h
+    uo = u.reshape(nT, N).astype(np.float64) - (pr - np.roll(pr, 1, axis=1)) / (h * np.sin(theta))[:, None]
+    vo = v.reshape(nT - 1, N).astype(np.float64) - (pr[1:] - pr[:-1]) / h
+    return uo.ravel(), vo.ravel(), pr.ravel()
+
+
+# ---- (1) phase-by-phase against the reference's own CUDA build ------------------------------
+
+@pytest.mark.parametrize("case", CASES)
+def test_initial_velocity_is_the_references(K, case):
+    g = oa.golden(case)
+    with make_solver(K, g, particles=False) as s:
+        st = state(s)
+    assert np.array_equal(st["velPhi"], g["init.velPhi"])
+    assert np.array_equal(st["velTheta"], g["init.velTheta"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_advection_vs_reference_dump(K, case):
+    g = oa.golden(case)
+    with make_solver(K, g) as s:
+        s.advection()
+        st = state(s)
+    for name in ("velPhi", "velTheta", "density", "particles"):
+        ref = g["s1_adv." + name]
+        e, w = oa.rel_l2(st[name], ref), words_equal(st[name], ref)
+        print("advection %s %-9s relL2 %.2e identical words %.5f" % (case, name, e, w))
+        assert e <= 1e-5
+        assert w >= 0.999
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_geometric_vs_reference_dump(K, case):
+    g = oa.golden(case)
+    with make_solver(K, g, particles=False) as s:
+        set_velocity(s, g["s1_adv.velPhi"], g["s1_adv.velTheta"])
+        s.geometric()
+        st = state(s)
+    for name in ("velPhi", "velTheta"):
+        ref = g["s1_geo." + name]
+        e, w = oa.rel_l2(st[name], ref), words_equal(st[name], ref)
+        print("geometric %s %-9s relL2 %.2e identical words %.5f" % (case, name, e, w))
+        assert e <= 1e-5
+        assert w >= 0.999
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_projection_vs_reference_dump(K, case):
+    g = oa.golden(case)
+    nT = int(g["meta.nTheta"])
+    N = 2 * nT
+    with make_solver(K, g, particles=False) as s:
+        set_velocity(s, g["s1_geo.velPhi"], g["s1_geo.velTheta"])
+        s.projection()
+        st = state(s)
+        pressure = s.pressure.copyBackToCPU().ravel().copy()
+    u64, v64, p64 = fp64_projection(nT, g["s1_geo.velPhi"], g["s1_geo.velTheta"])
+    ours = {"velPhi": st["velPhi"], "velTheta": st["velTheta"], "pressure": pressure}
+    exact = {"velPhi": u64, "velTheta": v64, "pressure": p64}
+    for name in ("velPhi", "velTheta", "pressure"):
+        ref = g["s1_proj." + name]
+        e_ref = oa.rel_l2(ours[name], ref)
+        e_ours64 = oa.rel_l2(ours[name], exact[name])
+        e_ref64 = oa.rel_l2(ref, exact[name])
+        print("projection %s %-9s vs reference %.2e | vs fp64: ours %.2e reference %.2e"
+              % (case, name, e_ref, e_ours64, e_ref64))
+        if name == "velPhi":
+            inner = slice(2 * N, (nT - 2) * N)
+            assert oa.rel_l2(ours[name][inner], ref[inner]) <= 1e-5
+            assert e_ours64 <= 3.0 * e_ref64 + 1e-6      # inside the reference's own fp32 noise
+            assert e_ref <= 4.0 * e_ref64 + 1e-6
+        else:
+            assert e_ref <= 1e-5
+
+
+@pytest.mark.parametrize("case", ["t16", "t32"])
+def test_second_step_phases_vs_reference_dump(K, case):
+    """Each phase of step 2 started from the reference's state (covers buffer-role swaps)."""
+    g = oa.golden(case)
+    nT = int(g["meta.nTheta"])
+    N = 2 * nT
+    with make_solver(K, g) as s:
+        set_velocity(s, g["s1_proj.velPhi"], g["s1_proj.velTheta"])
+        s.density.cpuBuffer[:] = g["s1_proj.density"].reshape(nT, N)
+        s.density.copyToGPU()
+        s.particles.coordCPUBuffer[:] = g["s1_proj.particles"]
+        s.particles.copy2GPU()
+        s.advection()
+        st = state(s)
+        for name in ("velPhi", "velTheta", "density", "particles"):
+            assert oa.rel_l2(st[name], g["s2_adv." + name]) <= 1e-5, name
+            assert words_equal(st[name], g["s2_adv." + name]) >= 0.999, name
+        set_velocity(s, g["s2_adv.velPhi"], g["s2_adv.velTheta"])
+        s.geometric()
+        st = state(s)
+        for name in ("velPhi", "velTheta"):
+            assert oa.rel_l2(st[name], g["s2_geo." + name]) <= 1e-5, name
+
+
+def test_free_run_divergence_100_steps(K):
+    """100-step free run at 128 x 256 against the reference's own 100-step dump: reported;
+    bounded loosely (chaotic amplification of fp32 round-off differences in the projection)."""
+    g = oa.golden("t128")
+    with make_solver(K, g) as s:
+        s.stepForward(nSteps=1)
+        st1 = state(s)
+        s.stepForward(nSteps=9)
+        st10 = state(s)
+        s.stepForward(nSteps=90)
+        st100 = state(s)
+    for tag, st in (("s1_proj", st1), ("s10_proj", st10), ("s100_proj", st100)):
+        for name in ("velPhi", "velTheta", "density", "particles"):
+            print("free run %-9s %-9s relL2 vs reference %.2e" % (tag, name, oa.rel_l2(st[name], g[tag + "." + name])))
+    assert oa.rel_l2(st1["velTheta"], g["s1_proj.velTheta"]) <= 1e-5
+    assert oa.rel_l2(st1["density"], g["s1_proj.density"]) <= 1e-5
+    assert oa.rel_l2(st1["particles"], g["s1_proj.particles"]) <= 1e-5
+    assert oa.rel_l2(st100["density"], g["s100_proj.density"]) <= 5e-2
+    assert oa.rel_l2(st100["velTheta"], g["s100_proj.velTheta"]) <= 2e-1
+    assert np.isfinite(st100["velPhi"]).all()
+
+
+# ---- (2) against the CPU oracle on the same inputs ---------------------------------------------
+
+@pytest.mark.parametrize("kind", [oa.VPHI, oa.VTHETA, oa.CENTERED])
+def test_sampler_indices_and_masks_bit_exact(K, kind):
+    """Cell indices, weights, validated coordinates and the flipped / pole-branch predicates of
+    the three samplers on adversarial coordinates: exactly the oracle's (IEEE-only) values."""
+    nT = 64
+    p = oa.params(nT)
+    h = float(p.gridLen)
+    rng = np.random.default_rng(11 + kind)
+    phi = rng.uniform(-2 * np.pi, 4 * np.pi, 20000).astype(np.float32)
+    theta = rng.uniform(-np.pi, 2 * np.pi, 20000).astype(np.float32)
+    edge_t = np.array([0.0, -0.0, h / 2, h, -h / 2, np.pi, np.pi - h / 2, np.pi + h / 2, np.pi - h, np.pi + h,
+                       2 * np.pi, np.float32(np.pi), np.nextafter(np.float32(np.pi), np.float32(4)),
+                       np.nextafter(np.float32(np.pi), np.float32(0)), 1e-30, -1e-30, (nT - 1) * h, (nT - 1.5) * h,
+                       (nT - 0.5) * h, 1.5 * h], dtype=np.float32)
+    edge_p = np.array([0.0, -1e-7, 2 * np.pi, np.float32(2 * np.pi), np.nextafter(np.float32(2 * np.pi), np.float32(0)),
+                       np.pi, -h / 2, h / 2, 2 * np.pi - h / 2, 4 * np.pi, -2 * np.pi, 127.5 * h], dtype=np.float32)
+    ep, et = np.meshgrid(edge_p, edge_t)
+    phi = np.concatenate([phi, ep.ravel()])
+    theta = np.concatenate([theta, et.ravel()])
+    with K.KaminoSolver(2 * nT, nT, 5.0, 0.005, initVelocity=False) as s:
+        got = s.locate(kind, phi, theta)
+    for k in range(phi.size):
+        loc = oa.locate(p, kind, float(phi[k]), float(theta[k]))
+        exp = (loc.phiIndex, loc.thetaIndex, np.float32(loc.alphaPhi), np.float32(loc.alphaTheta),
+               np.float32(loc.phi), np.float32(loc.theta), loc.flipped | (loc.poleBranch << 1))
+        have = (got["phiIndex"][k], got["thetaIndex"][k], got["alphaPhi"][k], got["alphaTheta"][k],
+                got["phi"][k], got["theta"][k], got["flags"][k])
+        assert all(np.asarray(a).tobytes() == np.asarray(b, dtype=np.asarray(a).dtype).tobytes() for a, b in zip(have, exp)), \
+            (k, float(phi[k]), float(theta[k]), have, exp)
+
+
+def test_one_step_at_c2_size_vs_oracle(K):
+    """512 x 1024 with density and 1,048,352 particles (BASELINE config 2): advection against the
+    oracle at full size."""
+    nT = 512
+    p = oa.params(nT)
+    u, v = oa.init_velocity(nT)
+    rho = oa.synthetic_density(nT)
+    pc = oa.seed_particles(nT, 2.0)
+    assert pc.size // 2 == 1048352
+    uo, vo, ro, po, _ = oa.step(p, u, v, rho, pc, phase=1)
+    with K.KaminoSolver(2 * nT, nT, 5.0, 0.005) as s:
+        s.density.cpuBuffer[:] = rho.reshape(nT, 2 * nT)
+        s.density.copyToGPU()
+        s.initParticlesfromPic("", 2)
+        assert np.array_equal(s.particles.coordCPUBuffer, pc)
+        s.advection()
+        st = state(s)
+    for name, ref in (("velPhi", uo), ("velTheta", vo), ("density", ro), ("particles", po)):
+        e = oa.rel_l2(st[name], ref)
+        print("C2 advection %-9s relL2 vs oracle %.2e" % (name, e))
+        assert e <= 1e-5
+
+
+# ---- (3) structure and properties ------------------------------------------------------------------
+
+def test_graph_steps_equal_phase_calls(K):
+    g = oa.golden("t32")
+    with make_solver(K, g) as a, make_solver(K, g) as b:
+        for _ in range(3):
+            a.advection(); a.geometric(); a.projection()
+        b.stepForward(nSteps=3)
+        b.sync()
+        sa, sb = state(a), state(b)
+    for name in sa:
+        assert np.array_equal(sa[name], sb[name]), name
+
+
+def test_step_chunking_is_consistent(K):
+    """kamino_step(13) (graphs of 10 + 2 + 1 steps) == 13 x kamino_step(1)."""
+    g = oa.golden("t16")
+    with make_solver(K, g) as a, make_solver(K, g) as b:
+        a.stepForward(nSteps=13)
+        for _ in range(13):
+            b.stepForward(nSteps=1)
+        sa, sb = state(a), state(b)
+    for name in sa:
+        assert np.array_equal(sa[name], sb[name]), name
+
+
+def test_ensemble_members_match_single_runs(K):
+    """batch = 3 simulations with different densities/particles in one context == 3 single runs."""
+    g = oa.golden("t32")
+    nT, N = 32, 64
+    rng = np.random.default_rng(3)
+    rhos = [g["init.density"].reshape(nT, N) * np.float32(1 + k) for k in range(3)]
+    parts = [np.stack([rng.uniform(0, 2 * np.pi, 1000), rng.uniform(0, np.pi, 1000)], axis=1).astype(np.float32).ravel()
+             for _ in range(3)]
+    vels = [(g["init.velPhi"] * np.float32(1 - 0.25 * k), g["init.velTheta"] * np.float32(1 + 0.5 * k)) for k in range(3)]
+    singles = []
+    for k in range(3):
+        with K.KaminoSolver(N, nT, 5.0, 0.005) as s:
+            set_velocity(s, *vels[k])
+            s.density.cpuBuffer[:] = rhos[k]; s.density.copyToGPU()
+            s.initParticlesfromPic("", 0, coords=parts[k])
+            s.stepForward(nSteps=4)
+            singles.append(state(s))
+    from kaminogpu_b200 import capi
+    with K.KaminoSolver(N, nT, 5.0, 0.005, batch=3) as s:
+        s.initParticlesfromPic("", 0, coords=parts[0])
+        for k in range(3):
+            for field, val in ((capi.VEL_PHI, vels[k][0]), (capi.VEL_THETA, vels[k][1]), (capi.DENSITY, rhos[k])):
+                q = s.quantity(field, k)
+                q.cpuBuffer[:] = np.asarray(val).reshape(q.cpuBuffer.shape)
+                q.copyToGPU()
+            capi.check(s._lib.kamino_upload_particles(s._ctx, k, parts[k].ctypes.data), s._ctx)
+        s.stepForward(nSteps=4)
+        for k in range(3):
+            for field, name in ((capi.VEL_PHI, "velPhi"), (capi.VEL_THETA, "velTheta"), (capi.DENSITY, "density")):
+                got = s.quantity(field, k).copyBackToCPU().ravel()
+                assert np.array_equal(got, singles[k][name]), (k, name)
+            pc = np.zeros(2000, np.float32)
+            capi.check(s._lib.kamino_download_particles(s._ctx, k, pc.ctypes.data), s._ctx)
+            assert np.array_equal(pc, singles[k]["particles"]), k
+
+
+def test_particle_tail_and_range(K):
+    """Particle counts that are not a multiple of the block size are handled (the reference has
+    no tail guard, kernel/KaminoCore.cu:323), coordinates stay in [0, 2 pi] x [0, pi]."""
+    g = oa.golden("t32")
+    rng = np.random.default_rng(5)
+    for n in (1, 255, 257, 1000):
+        pc = np.stack([rng.uniform(0, 2 * np.pi, n), rng.uniform(0, np.pi, n)], axis=1).astype(np.float32).ravel()
+        with make_solver(K, g, particles=False) as s:
+            s.initParticlesfromPic("", 0, coords=pc)
+            s.stepForward(nSteps=5)
+            out = s.particles.copyBack2CPU().reshape(-1, 2)
+        assert out.shape[0] == n and np.isfinite(out).all()
+        assert (out[:, 0] >= 0).all() and (out[:, 0] <= np.float32(2 * np.pi)).all()
+        assert (out[:, 1] >= 0).all() and (out[:, 1] <= np.float32(np.pi)).all()
+        p = oa.params(32)
+        _, _, _, po, _ = oa.step(p, g["init.velPhi"], g["init.velTheta"], None, pc, phase=1)
+        with make_solver(K, g, particles=False) as s:
+            s.initParticlesfromPic("", 0, coords=pc)
+            s.advection()
+            assert oa.rel_l2(s.particles.copyBack2CPU(), po) <= 1e-6
+
+
+def test_zero_particles_and_no_density_change(K):
+    g = oa.golden("t16")
+    with make_solver(K, g, particles=False) as s:
+        s.stepForward(nSteps=2)
+        st = state(s)
+    assert oa.rel_l2(st["velTheta"], g["s2_proj.velTheta"]) <= 1e-5
+    assert oa.rel_l2(st["density"], g["s2_proj.density"]) <= 1e-5
+
+
+def test_geometric_is_phi_shift_equivariant(K):
+    """The geometric update depends on theta only: rolling the input along phi rolls the output
+    (bit-exact)."""
+    g = oa.golden("t64")
+    nT, N = 64, 128
+    u = g["s1_adv.velPhi"].reshape(nT, N)
+    v = g["s1_adv.velTheta"].reshape(nT - 1, N)
+    outs = []
+    for shift in (0, 37):
+        with make_solver(K, g, particles=False) as s:
+            set_velocity(s, np.roll(u, shift, axis=1), np.roll(v, shift, axis=1))
+            s.geometric()
+            st = state(s)
+        outs.append((st["velPhi"].reshape(nT, N), st["velTheta"].reshape(nT - 1, N)))
+    assert np.array_equal(np.roll(outs[0][0], 37, axis=1), outs[1][0])
+    assert np.array_equal(np.roll(outs[0][1], 37, axis=1), outs[1][1])
+
+
+@pytest.mark.parametrize("nT", [512, 2048])
+def test_projection_properties_at_full_size(K, nT):
+    """BASELINE sizes (512 x 1024, 2048 x 4096): the projection is linear (P(2u) = 2 P(u) exactly
+    in binary floating point), removes most of the divergence, leaves a zonal (phi-independent)
+    flow untouched, and the pressure has zero zonal mean (n = 0 is never projected)."""
+    N = 2 * nT
+    p = oa.params(nT)
+    u, v = oa.init_velocity(nT)
+    with K.KaminoSolver(N, nT, 5.0, 0.005, initVelocity=False) as s:
+        def project(uu, vv):
+            set_velocity(s, uu, vv)
+            s.projection()
+            st = state(s)
+            return st["velPhi"], st["velTheta"], s.pressure.copyBackToCPU().copy()
+        u1, v1, p1 = project(u, v)
+        u2, v2, p2 = project(u * np.float32(2), v * np.float32(2))
+        assert np.array_equal(u2, u1 * np.float32(2)) and np.array_equal(v2, v1 * np.float32(2))
+        assert np.abs(p1.astype(np.float64).mean(axis=1)).max() <= 1e-5 * np.abs(p1).max()
+        d0 = np.zeros(nT * N, np.float32); d1 = np.zeros(nT * N, np.float32)
+        oa.lib().ko_divergence(ctypes.byref(p), oa.fptr(u), oa.fptr(v), oa.fptr(d0))
+        oa.lib().ko_divergence(ctypes.byref(p), oa.fptr(u1), oa.fptr(v1), oa.fptr(d1))
+        k0 = d0.reshape(nT, N)[2:-2].astype(np.float64); k1 = d1.reshape(nT, N)[2:-2].astype(np.float64)
+        k0 -= k0.mean(axis=1, keepdims=True); k1 -= k1.mean(axis=1, keepdims=True)
+        print("nTheta %d: non-zonal divergence norm %.3e -> %.3e" % (nT, np.linalg.norm(k0), np.linalg.norm(k1)))
+        assert np.linalg.norm(k1) <= 0.2 * np.linalg.norm(k0)
+        # zonal flow: u_phi depends on theta only, u_theta = 0 -> divergence has only n = 0 -> unchanged
+        uz = np.repeat(np.sin((np.arange(nT) + 0.5) * float(p.gridLen)).astype(np.float32), N)
+        vz = np.zeros((nT - 1) * N, np.float32)
+        u3, v3, p3 = project(uz, vz)
+        assert np.array_equal(u3, uz) and np.array_equal(v3, vz)
+
+
+@pytest.mark.parametrize("nT", [512, 2048])
+def test_advection_properties_at_full_size(K, nT):
+    """Uniform density stays uniform to 1 ulp; zero velocity is a fixed point of the whole step."""
+    N = 2 * nT
+    with K.KaminoSolver(N, nT, 5.0, 0.005) as s:
+        s.density.cpuBuffer[:] = np.float32(0.75)
+        s.density.copyToGPU()
+        s.advection()
+        rho = s.density.copyBackToCPU()
+        assert np.abs(rho - np.float32(0.75)).max() <= 6e-8
+    with K.KaminoSolver(N, nT, 5.0, 0.005, initVelocity=False) as s:
+        rho0 = oa.synthetic_density(nT).reshape(nT, N)
+        s.density.cpuBuffer[:] = rho0
+        s.density.copyToGPU()
+        s.stepForward(nSteps=2)
+        st = state(s)
+        assert not st["velPhi"].any() and not st["velTheta"].any()
+        assert oa.rel_l2(st["density"], rho0) <= 1e-6
+
+
+def test_run_frames_matches_stepping(K):
+    from kaminogpu_b200 import capi
+    g = oa.golden("t32")
+    nT, N = 32, 64
+    with make_solver(K, g) as a, make_solver(K, g) as b:
+        a.stepForward(nSteps=6)
+        sa = state(a)
+        n = b.particles.numOfParticles
+        hU = np.zeros(nT * N, np.float32); hV = np.zeros((nT - 1) * N, np.float32)
+        hR = np.zeros(nT * N, np.float32); hP = np.zeros(2 * n, np.float32)
+        capi.check(b._lib.kamino_run_frames(b._ctx, 2, 3, hU.ctypes.data, hV.ctypes.data, hR.ctypes.data,
+                                            hP.ctypes.data), b._ctx)
+    assert np.array_equal(hU, sa["velPhi"]) and np.array_equal(hV, sa["velTheta"])
+    assert np.array_equal(hR, sa["density"]) and np.array_equal(hP, sa["particles"])
+
+
+def test_error_reporting(K):
+    from kaminogpu_b200 import capi
+    with K.KaminoSolver(64, 32, 5.0, 0.005, initVelocity=False) as s:
+        buf = np.zeros(64 * 32, np.float32)
+        assert s._lib.kamino_upload_field(s._ctx, 9, 0, buf.ctypes.data) == capi_err("INVALID")
+        assert s._lib.kamino_upload_field(s._ctx, 0, 5, buf.ctypes.data) == capi_err("INVALID")
+        assert b"range" in s._lib.kamino_last_error(s._ctx)
+        assert s._lib.kamino_step(s._ctx, -1) == capi_err("INVALID")
+
+
+def capi_err(name):
+    return {"INVALID": 10001, "NO_DEVICE": 10002, "STATE": 10003}[name]
+
+
+def test_cli_runs_config_file(K, tmp_path):
+    """The compiled drop-in: `kamino configKamino.txt` with the reference's grammar, output on,
+    produces gzip'd .bgeo frames and the reference's progress lines."""
+    import gzip
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = tmp_path / "configKamino.txt"
+    (tmp_path / "out").mkdir()
+    cfg.write_text("5.0 32 4.0 0.005 0.041666668 2 0.0 1 1 1 1 %s/out/f %s/out/p null null null\n" % (tmp_path, tmp_path))
+    out = subprocess.run([os.path.join(root, "kaminogpu_b200", "kamino"), str(cfg)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "Frame 2 is ready" in out.stdout and "frames per second" in out.stdout
+    for stem, npts in (("f", 32 * 64), ("p", 8192)):
+        for frame in (0, 1, 2):
+            raw = gzip.open(str(tmp_path / "out" / ("%s%d.bgeo" % (stem, frame)))).read()
+            assert raw[:5] == b"BgeoV"
+            version, points = struct.unpack(">ii", raw[5:13])
+            assert version == 5 and points == npts
