@@ -8,12 +8,16 @@ Tolerances (fp32 relative L2 per field, north star: <= 1e-5 per field per step):
       arithmetic operation for operation and are expected bit-identical on the goldens
       (asserted as >= 99.9% identical words so that a single double-rounding tie cannot
       fail the suite; the exact fraction is printed).
-  projection: u_theta and pressure 1e-5. u_phi: 1e-5 away from the two rows next to each
-      pole; in those rows the phi gradient divides the fp32 round-off of p by
-      h*sin(theta) (3e-4 at nTheta=128), so two correct fp32 evaluations of the same operator
-      (cuFFT + transposes vs our FFT) differ by ~1e-3 there. The bound used for the whole
-      field is "no worse than 3x the reference's own distance from an fp64 evaluation"
-      (see DESIGN.md "projection parity").
+  projection: u_theta and pressure 1e-5 against the reference dump. u_phi: the reference's own
+      result is 5e-6 (nTheta=16) .. 8e-4 (nTheta=128) away from an fp64 evaluation of its own
+      operator: it adds the n = 0 "identity solve" mode (the zonal-mean divergence, O(100)) into
+      every pressure value inside cuFFT and subtracts it again (kernel/KaminoCore.cu:692-700),
+      which leaves ~|U_0| * 2^-24 of absolute noise in p, and the phi gradient divides that by
+      h*sin(theta) (3e-4 in the polar rows at nTheta=128). That noise depends on cuFFT's internal
+      rounding and cannot be reproduced by any other FFT. Asserted instead: (a) our u_phi, u_theta
+      and p are within 1e-5 of the fp64 evaluation (measured ~1e-6, i.e. ~500x closer than the
+      reference is), and (b) |ours - reference| <= 1.5 x |reference - fp64| (the whole distance
+      is the reference's own noise). See DESIGN.md "projection parity".
 """
 import ctypes
 
@@ -150,11 +154,11 @@ def test_projection_vs_reference_dump(K, case):
         e_ref64 = oa.rel_l2(ref, exact[name])
         print("projection %s %-9s vs reference %.2e | vs fp64: ours %.2e reference %.2e"
               % (case, name, e_ref, e_ours64, e_ref64))
+        # (a) closer to the exact operator than the north-star tolerance
+        assert e_ours64 <= 1e-5
+        # (b) the distance to the reference is the reference's own fp32 noise, not ours
         if name == "velPhi":
-            inner = slice(2 * N, (nT - 2) * N)
-            assert oa.rel_l2(ours[name][inner], ref[inner]) <= 1e-5
-            assert e_ours64 <= 3.0 * e_ref64 + 1e-6      # inside the reference's own fp32 noise
-            assert e_ref <= 4.0 * e_ref64 + 1e-6
+            assert e_ref <= 1.5 * e_ref64 + 1e-6
         else:
             assert e_ref <= 1e-5
 
@@ -452,6 +456,50 @@ def test_error_reporting(K):
 
 def capi_err(name):
     return {"INVALID": 10001, "NO_DEVICE": 10002, "STATE": 10003}[name]
+
+
+def test_live_reference_build_at_c2_size(K, tmp_path):
+    """Run the reference's own CUDA build (oracle/_ref/kamino_ref, compiled from /root/reference
+    by oracle/ref_harness) HERE on 512 x 1024 with 1,048,352 particles and compare phase by
+    phase from its own states: advection, particles and geometric bit-identical at full size."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "kamino_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/kamino_ref not built (needs /root/reference at build time)")
+    nT, N = 512, 1024
+    out = subprocess.run([exe, "dump", str(nT), "2", "0.005", "5.0", "1", str(tmp_path), "-", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    ld = lambda tag, f: np.fromfile(str(tmp_path / ("%s.%s.f32" % (tag, f))), dtype=np.float32)
+    with K.KaminoSolver(N, nT, 5.0, 0.005) as s:
+        assert np.array_equal(s.velPhi.cpuBuffer.ravel(), ld("init", "velPhi"))
+        s.density.cpuBuffer[:] = ld("init", "density").reshape(nT, N)
+        s.density.copyToGPU()
+        s.initParticlesfromPic("", 2)
+        assert np.array_equal(s.particles.coordCPUBuffer, ld("init", "particles"))
+        s.advection()
+        st = state(s)
+        for name in ("velPhi", "velTheta", "density", "particles"):
+            w = words_equal(st[name], ld("s1_adv", name))
+            print("live reference C2 advection %-9s identical words %.6f" % (name, w))
+            assert oa.rel_l2(st[name], ld("s1_adv", name)) <= 1e-5 and w >= 0.9999
+        s.geometric()
+        st = state(s)
+        for name in ("velPhi", "velTheta"):
+            w = words_equal(st[name], ld("s1_geo", name))
+            print("live reference C2 geometric %-9s identical words %.6f" % (name, w))
+            assert oa.rel_l2(st[name], ld("s1_geo", name)) <= 1e-5 and w >= 0.9999
+        s.projection()
+        st = state(s)
+        pr = s.pressure.copyBackToCPU().ravel()
+        u64, v64, p64 = fp64_projection(nT, ld("s1_geo", "velPhi"), ld("s1_geo", "velTheta"))
+        for name, got, exact in (("velPhi", st["velPhi"], u64), ("velTheta", st["velTheta"], v64), ("pressure", pr, p64)):
+            e_ref, e64, r64 = oa.rel_l2(got, ld("s1_proj", name)), oa.rel_l2(got, exact), oa.rel_l2(ld("s1_proj", name), exact)
+            print("live reference C2 projection %-9s vs reference %.2e | vs fp64: ours %.2e reference %.2e" % (name, e_ref, e64, r64))
+            assert e64 <= 1e-5 or e64 <= r64
+            assert e_ref <= 1.5 * r64 + 1e-6
 
 
 def test_cli_runs_config_file(K, tmp_path):
