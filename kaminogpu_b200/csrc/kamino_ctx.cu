@@ -6,8 +6,10 @@
 //   pressure                             batch x nTheta x nPhi fp32
 //   spectrum                             batch x nTheta x nPhi/2 float2 (half spectrum)
 //   particles[2]                         batch x numParticles float2, double-buffered
-//   tables                               twiddles + per-row constants
-// = 36 B/cell + 16 B/particle (the reference: 76 B/cell).
+//   tables                               twiddles + per-row constants + the cyclic-reduction
+//                                        factors of every wavenumber (20 B per cell, read-only)
+// = 36 B/cell of state + 20 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
+// SURVEY.md appendix B).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -121,7 +123,7 @@ cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 
 cudaError_t enqueueGeometric(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
-    cudaError_t e = launchGeometric(ctx->g, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
+    cudaError_t e = launchGeometric(ctx->g, ctx->tables, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
                                     ctx->velPhi[st.vel ^ 1], ctx->velTheta[st.vel ^ 1], ctx->batch, s);
     st.vel ^= 1;                                          // kernel/KaminoCore.cu:582
     return e;
@@ -317,6 +319,12 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         ctx->tables.triA = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.triC = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.sinSq = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.geoG = (float*)sub(sizeof(float) * nTheta);
+        const size_t slotRows = (size_t)nTheta * (g.nPhi / 2);
+        ctx->tables.crFwd = (float2*)sub(sizeof(float2) * slotRows);
+        ctx->tables.crA = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.crB = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.crC = (float*)sub(sizeof(float) * slotRows);
         ctx->tables.minusTwoOverH2 = -2.0 / (double)(g.h * g.h);
     }
 
@@ -328,6 +336,7 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
     ctx->stream = ctx->ownStream;
     if (ok) ok = configureKernels(g) == cudaSuccess;
     if (ok) ok = launchBuildTables(g, ctx->tables, ctx->stream) == cudaSuccess;
+    if (ok) ok = launchBuildCrTables(g, ctx->tables, ctx->stream) == cudaSuccess;
     if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     if (ok) ok = allocParticles(ctx, particlesPerSim) == 0;
     if (!ok) {

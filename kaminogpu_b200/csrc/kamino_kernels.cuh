@@ -24,11 +24,8 @@ cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phi
                          int* phiIndex, int* thetaIndex, float* alphaPhi, float* alphaTheta,
                          float* phiOut, float* thetaOut, int* flags, cudaStream_t stream);
 
-// geometric phase: velPhi/velTheta (this) -> velPhiOut/velThetaOut (next)
-cudaError_t launchGeometric(const GridParams& g, const float* velPhi, const float* velTheta,
-                            float* velPhiOut, float* velThetaOut, int batch, cudaStream_t stream);
-
-// Per-context read-only tables for the projection (built once by launchBuildTables).
+// Per-context read-only per-row tables (built once by launchBuildTables with the same device
+// functions the reference's kernels call per thread, so every entry is bit-identical).
 struct SpectralTables {
     float2* twiddle;      // nPhi entries: exp(-2 pi i k / nPhi)
     float* divFactor;     // nTheta: invGridSine / gridLen        (kernel/KaminoCore.cu:625,628)
@@ -38,10 +35,24 @@ struct SpectralTables {
     float* triA;          // nTheta: sub-diagonal before the Neumann fold (KaminoSolver.cu:135-136)
     float* triC;          // nTheta: super-diagonal               (:137-138)
     float* sinSq;         // nTheta: sinf(theta_j)^2              (:134)
+    float* geoG;          // nTheta: dt*cosf(theta_j)/(R*sinf(theta_j))   (kernel/KaminoCore.cu:494)
     double minusTwoOverH2;  // -2.0 / (h*h)                        (:133)
+    // cyclic-reduction factors of every wavenumber slot (tridiag.cu), layout [.][slot]
+    float2* crFwd;        // nTheta x N/2: (tmp1, tmp2) of forward level l, element idx at row nTheta-(nTheta>>l)+idx
+    float* crA;           // nTheta x N/2: a, b, c of every row after the forward elimination
+    float* crB;
+    float* crC;
 };
 
+// geometric phase: velPhi/velTheta (this) -> velPhiOut/velThetaOut (next)
+cudaError_t launchGeometric(const GridParams& g, const SpectralTables& t, const float* velPhi, const float* velTheta,
+                            float* velPhiOut, float* velThetaOut, int batch, cudaStream_t stream);
+
 size_t spectralTableBytes(const GridParams& g);
+size_t crTableFloats(const GridParams& g);
+cudaError_t configureTridiagonal(const GridParams& g);
+// runs after launchBuildTables (same stream): cyclic reduction of the coefficients, once
+cudaError_t launchBuildCrTables(const GridParams& g, SpectralTables t, cudaStream_t stream);
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream);
 
 // spectrum layout: S[sim][j][k], k = 0 .. nPhi/2-1, float2; slot k holds wavenumber

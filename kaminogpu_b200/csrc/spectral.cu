@@ -14,71 +14,50 @@
 // The divergence is real, so only n = 1 .. N/2 is needed (U_-n = conj U_n); the half
 // spectrum of a row is N/2 complex values, stored with the Nyquist mode in slot 0.
 //
-// FFT strategy: every transform is ONE complex FFT of length N per block, staged in shared
-// memory (Stockham autosort, radix 4, twiddles from a read-only table):
+// FFT strategy: every transform is ONE complex FFT of length N executed by N/16 threads, 16
+// values per thread in registers, radix-16 Stockham passes through padded shared memory
+// (fft_core.cuh: N = 1024 is 4 x 16 x 16, N = 4096 is 16 x 16 x 16), twiddles from a table:
 //   forward : two divergence rows are packed as z = div_j + i div_{j+1}; their spectra are
 //             separated with the Hermitian symmetry.
 //   inverse : row j needs p_j (for the phi gradient) and p_{j+1} - p_j (for the theta
 //             gradient). By linearity both come from one transform of X + iY with
 //             X = U_j, Y = U_{j+1} - U_j, so no block ever needs another block's output.
 #include "kamino_kernels.cuh"
+#include "fft_core.cuh"
+#include "tma_bulk.cuh"
 
 namespace kb {
 
 namespace {
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
-{
-    return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
-}
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-
-// In-place-semantics complex FFT of length N held in shared memory, executed by N/4
-// threads (tid = 0 .. N/4-1). `a` holds the input, `b` is scratch of the same size; returns
-// the buffer that holds the result (natural order). SIGN = -1: exp(-2 pi i k m / N).
-// Callers must __syncthreads() after filling `a`; the result is synchronised on return.
+// Complex FFT of length N by the T = N/16 threads of one transform (t = 0 .. T-1), entirely
+// from registers: on entry v[e] = x[t + e*T]; on exit v[m] = X[t + m*T] and the whole
+// spectrum also sits in `buf` (padded shared memory, natural order, synchronised).
+// Every thread of the block must call this (it contains __syncthreads()).
+// `tw` is the twiddle table (global, or its shared-memory copy once `twReady` has completed:
+// the first pass needs no twiddles, so the wait sits after it).
 template <int SIGN>
-__device__ __forceinline__ float2* fftShared(float2* a, float2* b, int N, int log2N, int tid,
-                                             const float2* __restrict__ twiddle)
+__device__ __forceinline__ void fftFromRegisters(float2* v, float2* buf, int t, int T, int N, int log2N,
+                                                 const float2* tw, uint64_t* twReady)
 {
-    const int quarter = N >> 2;
-    int Ns = 1;
-    if (log2N & 1) {
-        // leading radix-2 stage: two butterflies per thread
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = tid + h * quarter;
-            const float2 v0 = a[j], v1 = a[j + (N >> 1)];
-            b[2 * j] = cadd(v0, v1);
-            b[2 * j + 1] = csub(v0, v1);
-        }
-        float2* t = a; a = b; b = t;
-        Ns = 2;
-        __syncthreads();
+    using namespace fft;
+    int Ns;
+    switch (log2N & 3) {
+    case 1: passCompute<SIGN, 2>(v, t, T, N, 1, tw); passScatter<2>(v, buf, t, T, 1); Ns = 2; break;
+    case 2: passCompute<SIGN, 4>(v, t, T, N, 1, tw); passScatter<4>(v, buf, t, T, 1); Ns = 4; break;
+    case 3: passCompute<SIGN, 8>(v, t, T, N, 1, tw); passScatter<8>(v, buf, t, T, 1); Ns = 8; break;
+    default: passCompute<SIGN, 16>(v, t, T, N, 1, tw); passScatter<16>(v, buf, t, T, 1); Ns = 16; break;
     }
+    if (twReady) tma::mbarWait(twReady, 0);
+    __syncthreads();
     while (Ns < N) {
-        const int k = tid & (Ns - 1);
-        const int base = k * (N / (4 * Ns));
-        float2 v0 = a[tid], v1 = a[tid + quarter], v2 = a[tid + 2 * quarter], v3 = a[tid + 3 * quarter];
-        if (Ns > 1) {
-            float2 w1 = __ldg(twiddle + base), w2 = __ldg(twiddle + 2 * base), w3 = __ldg(twiddle + 3 * base);
-            if (SIGN > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-            v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
-        }
-        const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3);
-        const float2 d = csub(v1, v3);
-        const float2 a3 = (SIGN < 0) ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x);
-        const int idx = ((tid - k) << 2) + k;
-        b[idx] = cadd(a0, a2);
-        b[idx + Ns] = cadd(a1, a3);
-        b[idx + 2 * Ns] = csub(a0, a2);
-        b[idx + 3 * Ns] = csub(a1, a3);
-        float2* t = a; a = b; b = t;
-        Ns <<= 2;
+        passGather(v, buf, t, T);
+        __syncthreads();                       // everyone has read before anyone overwrites
+        passCompute<SIGN, 16>(v, t, T, N, Ns, tw);
+        passScatter<16>(v, buf, t, T, Ns);
+        Ns <<= 4;
         __syncthreads();
     }
-    return a;
 }
 
 // ---- tables ---------------------------------------------------------------------------
@@ -109,6 +88,8 @@ __global__ void buildTablesKernel(GridParams g, SpectralTables t)
         t.triA[k] = (float)(1.0 / h2 - cot);
         t.triC[k] = (float)(1.0 / h2 + cot);
         t.sinSq[k] = __fmul_rn(sinT, sinT);
+        // geometricFillKernel, kernel/KaminoCore.cu:494
+        t.geoG[k] = __fdiv_rn(__fmul_rn(g.dt, cosT), __fmul_rn(g.radius, sinT));
     }
 }
 
@@ -131,43 +112,99 @@ __device__ __forceinline__ float divergenceAt(const GridParams& g, const Spectra
     return __fmaf_rn(factor, __fsub_rn(uEast, uWest), termTheta);
 }
 
-// grid (nTheta/2, batch), block N/4 threads, dynamic smem 2 * N * sizeof(float2)
-__global__ void divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ velPhiAll,
-                                    const float* __restrict__ velThetaAll, float2* __restrict__ spectrumAll)
+// Shared-memory twiddle staging: one thread starts a TMA bulk copy of the N-entry table
+// (N * 8 bytes, L2-resident) while everybody loads its inputs; the table is first needed by
+// the second pass. Returns the barrier to wait on (NULL when the table stays in global memory).
+template <bool STAGE>
+__device__ __forceinline__ uint64_t* stageTwiddles(const float2* __restrict__ twGlobal, float2* twShared,
+                                                   uint64_t* bar, int N)
 {
-    extern __shared__ float2 smem[];
-    const int N = g.nPhi, half = N >> 1;
-    float2* bufA = smem;
-    float2* bufB = smem + N;
+    if (!STAGE) return nullptr;
+    if (threadIdx.x == 0) { tma::mbarInit(bar, 1); tma::fenceBarrierInit(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbarExpectTx(bar, (uint32_t)(N * sizeof(float2)));
+        tma::bulkLoad(twShared, twGlobal, (uint32_t)(N * sizeof(float2)), bar);
+    }
+    return bar;
+}
+
+// Each transform handles a pair of theta rows (z = div_j + i div_{j+1}) with T = N/16 threads;
+// a block of BLOCK threads holds BLOCK/T transforms. grid (ceil(nTheta/2 / (BLOCK/T)), batch),
+// dynamic smem: [twiddles N float2 if STAGE] + (BLOCK/T) * paddedSize(N) float2.
+template <int BLOCK, bool STAGE>
+__global__ void __launch_bounds__(BLOCK)
+divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ velPhiAll,
+                    const float* __restrict__ velThetaAll, float2* __restrict__ spectrumAll)
+{
+    extern __shared__ __align__(16) float2 smem[];
+    __shared__ __align__(8) uint64_t twBar;
+    const int N = g.nPhi, half = N >> 1, log2T = g.log2NPhi - 4, T = 1 << log2T;
+    const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
+    const int pairs = g.nTheta >> 1;
+    const int pairRaw = blockIdx.x * (BLOCK >> log2T) + local;
+    const bool valid = pairRaw < pairs;
+    const int j = 2 * (valid ? pairRaw : pairs - 1);
+    float2* twShared = smem;
+    float2* buf = smem + (STAGE ? N : 0) + (size_t)local * fft::paddedSize(N);
     const int sim = blockIdx.y;
     const float* velPhi = velPhiAll + (size_t)sim * g.cells;
     const float* velTheta = velThetaAll + (size_t)sim * g.cells;
     float2* spectrum = spectrumAll + (size_t)sim * (g.cells >> 1);
-    const int j = 2 * blockIdx.x;
-    const int tid = threadIdx.x;
 
+    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, N);
+    const float2* tw = STAGE ? twShared : t.twiddle;
+
+    // divergence of rows j and j + 1 (fillDivergenceKernel, kernel/KaminoCore.cu:598-632) at the
+    // 16 columns i = tt + e*T of this thread; all loads of a half are issued before they are used
+    const float* uA = velPhi + (size_t)j * N;                  // u_phi rows j, j+1
+    const float* uB = uA + N;
+    const float* vN = velTheta + (size_t)(j > 0 ? j - 1 : 0) * N;             // u_theta rows j-1, j, j+1
+    const float* vM = velTheta + (size_t)j * N;
+    const float* vS = velTheta + (size_t)(j + 1 < g.nTheta - 1 ? j + 1 : j) * N;
+    const float nMask = j > 0 ? 1.0f : 0.0f;                    // v_N = 0 on the first row
+    const float sMask = (j + 1 < g.nTheta - 1) ? 1.0f : 0.0f;   // v_S = 0 on the last row
+    const float facA = __ldg(t.divFactor + j), facB = __ldg(t.divFactor + j + 1);
+    const float snA = __ldg(t.sinNorth + j), ssA = __ldg(t.sinSouth + j);
+    const float snB = __ldg(t.sinNorth + j + 1), ssB = __ldg(t.sinSouth + j + 1);
+    float2 v[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = tid + r * (N >> 2);
-        bufA[i] = make_float2(divergenceAt(g, t, velPhi, velTheta, j, i),
-                              divergenceAt(g, t, velPhi, velTheta, j + 1, i));
+    for (int h = 0; h < 2; ++h) {
+        float a0[8], a1[8], b0[8], b1[8], c0[8], c1[8], c2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = tt + ((h * 8 + e) << log2T);
+            const int ie = (i + 1) & (N - 1);
+            a0[e] = __ldg(uA + i); a1[e] = __ldg(uA + ie);
+            b0[e] = __ldg(uB + i); b1[e] = __ldg(uB + ie);
+            c0[e] = __ldg(vN + i); c1[e] = __ldg(vM + i); c2[e] = __ldg(vS + i);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float vn = c0[e] * nMask, vs = c2[e] * sMask;
+            const float termA = __fmul_rn(facA, __fmaf_rn(c1[e], ssA, -__fmul_rn(vn, snA)));
+            const float termB = __fmul_rn(facB, __fmaf_rn(vs, ssB, -__fmul_rn(c1[e], snB)));
+            v[h * 8 + e] = make_float2(__fmaf_rn(facA, __fsub_rn(a1[e], a0[e]), termA),
+                                       __fmaf_rn(facB, __fsub_rn(b1[e], b0[e]), termB));
+        }
     }
-    __syncthreads();
-    const float2* Z = fftShared<-1>(bufA, bufB, N, g.log2NPhi, tid, t.twiddle);
+    fftFromRegisters<-1>(v, buf, tt, T, N, g.log2NPhi, tw, twReady);
 
-    // separate the two real rows and scale by 1/N (shiftFKernel, kernel/KaminoCore.cu:652-653)
+    // v[m] = Z[tt + m*T]. Separate the two real rows and scale by 1/N (shiftFKernel,
+    // kernel/KaminoCore.cu:652-653); only k = 1 .. N/2 is kept, the Nyquist mode in slot 0.
+    if (!valid) return;
     const float scale = 0.5f / (float)N;
     float2* rowA = spectrum + (size_t)j * half;
     float2* rowB = spectrum + (size_t)(j + 1) * half;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int k = tid + r * (N >> 2);          // 0 .. N/2-1
+    for (int m = 0; m < 8; ++m) {
+        const int k = tt + (m << log2T);          // 0 .. N/2-1
         if (k == 0) {
-            const float2 zn = Z[half];               // Nyquist: both rows real
+            const float2 zn = v[8];                // Z[N/2] (tt = 0): both rows real
             rowA[0] = make_float2(2.0f * scale * zn.x, 0.0f);
             rowB[0] = make_float2(2.0f * scale * zn.y, 0.0f);
         } else {
-            const float2 zk = Z[k], zc = Z[N - k];
+            const float2 zk = v[m], zc = buf[fft::pad(N - k)];
             // A_k = (Z_k + conj Z_{N-k}) / 2,  B_k = (Z_k - conj Z_{N-k}) / (2i)
             rowA[k] = make_float2(scale * (zk.x + zc.x), scale * (zk.y - zc.y));
             rowB[k] = make_float2(scale * (zk.y + zc.y), scale * (zc.x - zk.x));
@@ -175,192 +212,94 @@ __global__ void divergenceFFTKernel(GridParams g, SpectralTables t, const float*
     }
 }
 
-// ---- K5: tridiagonal solves (cyclic reduction in the reference's elimination order) ----
-
-__device__ __forceinline__ int padIdx(int i) { return i + (i >> 5); }
-
-// grid (N/2 / W, batch), block W * nTheta/2 threads. Each block solves W wavenumber slots,
-// real and imaginary right-hand sides together (the reference runs crKernel twice and
-// reloads a, b, c, kernel/KaminoCore.cu:779-792). Coefficients are generated in the kernel
-// from per-row tables (precomputeABCKernel, kernel/KaminoSolver.cu:117-163).
-__global__ void tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int W)
-{
-    extern __shared__ float smemF[];
-    const int nT = g.nTheta, N = g.nPhi, half = N >> 1;
-    const int L = nT + (nT >> 5) + 1;               // padded length of one array
-    const int tid = threadIdx.x;
-    const int w = tid % W;                          // which system of this block
-    const int th = tid / W;                         // 0 .. nT/2-1
-    float* a = smemF + (size_t)w * 7 * L;
-    float* b = a + L;
-    float* c = b + L;
-    float* dr = c + L;
-    float* di = dr + L;
-    float* xr = di + L;
-    float* xi = xr + L;
-
-    float2* spectrum = spectrumAll + (size_t)blockIdx.y * (g.cells >> 1);
-    const int slot = blockIdx.x * W + w;
-    const int n = (slot == 0) ? half : slot;        // wavenumber of this slot (never 0)
-    const float nSq = (float)(n * n);
-
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int i = th + r * (nT >> 1);
-        float valA = __ldg(t.triA + i), valC = __ldg(t.triC + i);
-        float valB = (float)(t.minusTwoOverH2 - (double)__fdiv_rn(nSq, __ldg(t.sinSq + i)));
-        if (i == 0) { valB = __fadd_rn(valB, valA); valA = 0.0f; }
-        if (i == nT - 1) { valB = __fadd_rn(valB, valC); valC = 0.0f; }
-        const float2 f = spectrum[(size_t)i * half + slot];
-        const int p = padIdx(i);
-        a[p] = valA; b[p] = valB; c[p] = valC; dr[p] = f.x; di[p] = f.y;
-    }
-
-    // forward elimination, kernel/tdm.cu:43-63
-    int stride = 1;
-    int numThreads = nT >> 1;
-    int iteration = 0;
-    while ((2 << iteration) < nT) ++iteration;      // log2(nT / 2)
-    for (int lvl = 0; lvl < iteration; ++lvl) {
-        __syncthreads();
-        stride <<= 1;
-        const int delta = stride >> 1;
-        if (th < numThreads) {
-            const int i = stride * th + stride - 1;
-            const int iLeft = i - delta;
-            int iRight = i + delta;
-            if (iRight >= nT) iRight = nT - 1;
-            const int pi = padIdx(i), pl = padIdx(iLeft), pr = padIdx(iRight);
-            const float tmp1 = __fdiv_rn(a[pi], b[pl]);
-            const float tmp2 = __fdiv_rn(c[pi], b[pr]);
-            const float bi = __fmaf_rn(a[pr], -tmp2, __fmaf_rn(c[pl], -tmp1, b[pi]));
-            const float dri = __fmaf_rn(dr[pr], -tmp2, __fmaf_rn(dr[pl], -tmp1, dr[pi]));
-            const float dii = __fmaf_rn(di[pr], -tmp2, __fmaf_rn(di[pl], -tmp1, di[pi]));
-            const float ai = __fmul_rn(a[pl], -tmp1);
-            const float ci = __fmul_rn(c[pr], -tmp2);
-            b[pi] = bi; dr[pi] = dri; di[pi] = dii; a[pi] = ai; c[pi] = ci;
-        }
-        numThreads >>= 1;
-    }
-    __syncthreads();
-    // 2 x 2 system, kernel/tdm.cu:65-72
-    if (th < 2) {
-        const int p1 = padIdx(stride - 1), p2 = padIdx(2 * stride - 1);
-        const float det = __fmaf_rn(b[p2], b[p1], -__fmul_rn(c[p1], a[p2]));
-        if (th == 0) {
-            xr[p1] = __fdiv_rn(__fmaf_rn(b[p2], dr[p1], -__fmul_rn(c[p1], dr[p2])), det);
-            xi[p1] = __fdiv_rn(__fmaf_rn(b[p2], di[p1], -__fmul_rn(c[p1], di[p2])), det);
-        } else {
-            xr[p2] = __fdiv_rn(__fmaf_rn(dr[p2], b[p1], -__fmul_rn(dr[p1], a[p2])), det);
-            xi[p2] = __fdiv_rn(__fmaf_rn(di[p2], b[p1], -__fmul_rn(di[p1], a[p2])), det);
-        }
-    }
-    // back substitution, kernel/tdm.cu:75-90
-    numThreads = 2;
-    for (int lvl = 0; lvl < iteration; ++lvl) {
-        const int delta = stride >> 1;
-        __syncthreads();
-        if (th < numThreads) {
-            const int i = stride * th + (stride >> 1) - 1;
-            const int pi = padIdx(i), pp = padIdx(i + delta);
-            if (i == delta - 1) {
-                xr[pi] = __fdiv_rn(__fmaf_rn(-c[pi], xr[pp], dr[pi]), b[pi]);
-                xi[pi] = __fdiv_rn(__fmaf_rn(-c[pi], xi[pp], di[pi]), b[pi]);
-            } else {
-                const int pm = padIdx(i - delta);
-                xr[pi] = __fdiv_rn(__fmaf_rn(-c[pi], xr[pp], __fmaf_rn(-a[pi], xr[pm], dr[pi])), b[pi]);
-                xi[pi] = __fdiv_rn(__fmaf_rn(-c[pi], xi[pp], __fmaf_rn(-a[pi], xi[pm], di[pi])), b[pi]);
-            }
-        }
-        stride >>= 1;
-        numThreads <<= 1;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int i = th + r * (nT >> 1);
-        const int p = padIdx(i);
-        spectrum[(size_t)i * half + slot] = make_float2(xr[p], xi[p]);
-    }
-}
-
 // ---- K6: inverse FFT + gradient subtraction ---------------------------------------------
 
-// grid (nTheta, batch), block N/4 threads, dynamic smem 2 * N * sizeof(float2)
-__global__ void inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restrict__ spectrumAll,
-                                         float* __restrict__ velPhiAll, float* __restrict__ velThetaAll,
-                                         float* __restrict__ pressureAll)
+// One transform per theta row with T = N/16 threads, BLOCK/T rows per block.
+// grid (ceil(nTheta / (BLOCK/T)), batch), dynamic smem as for the forward kernel.
+template <int BLOCK, bool STAGE>
+__global__ void __launch_bounds__(BLOCK)
+inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restrict__ spectrumAll,
+                         float* __restrict__ velPhiAll, float* __restrict__ velThetaAll,
+                         float* __restrict__ pressureAll)
 {
-    extern __shared__ float2 smem[];
-    const int N = g.nPhi, half = N >> 1, nT = g.nTheta;
-    float2* bufA = smem;
-    float2* bufB = smem + N;
+    extern __shared__ __align__(16) float2 smem[];
+    __shared__ __align__(8) uint64_t twBar;
+    const int N = g.nPhi, half = N >> 1, nT = g.nTheta, log2T = g.log2NPhi - 4, T = 1 << log2T;
+    const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
+    const int rowRaw = blockIdx.x * (BLOCK >> log2T) + local;
+    const bool valid = rowRaw < nT;
+    const int j = valid ? rowRaw : nT - 1;
+    float2* twShared = smem;
+    float2* buf = smem + (STAGE ? N : 0) + (size_t)local * fft::paddedSize(N);
     const int sim = blockIdx.y;
     const float2* spectrum = spectrumAll + (size_t)sim * (g.cells >> 1);
-    float* velPhi = velPhiAll + (size_t)sim * g.cells;
-    float* velTheta = velThetaAll + (size_t)sim * g.cells;
-    const int j = blockIdx.x;
-    const int tid = threadIdx.x;
+    float* velPhi = velPhiAll + (size_t)sim * g.cells + (size_t)j * N;
+    float* velTheta = velThetaAll + (size_t)sim * g.cells + (size_t)j * N;
     const bool hasSouth = (j < nT - 1);
     const float2* rowU = spectrum + (size_t)j * half;
-    const float2* rowS = spectrum + (size_t)(hasSouth ? j + 1 : j) * half;
+    const float2* rowS = spectrum + (size_t)(hasSouth ? j + 1 : j) * half;     // !hasSouth: Y = 0
 
-    // W_k = X_k + i Y_k with X = U_j, Y = U_{j+1} - U_j (Hermitian completions), X_0 = Y_0 = 0
+    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, N);
+    const float2* tw = STAGE ? twShared : t.twiddle;
+
+    // W_k = X_k + i Y_k with X = U_j, Y = U_{j+1} - U_j (Hermitian completions), X_0 = Y_0 = 0.
+    // Thread tt needs W at idx = tt + e*T: for idx < N/2 from slot idx, for idx > N/2 from the
+    // mirrored slot N - idx, for idx = N/2 from slot 0 (the Nyquist mode, real parts only).
+    float2 v[16];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int k = tid + r * (N >> 2);
-        const float2 x = rowU[k];
-        float2 y = make_float2(0.0f, 0.0f);
-        if (hasSouth) { const float2 s = rowS[k]; y = make_float2(s.x - x.x, s.y - x.y); }
-        if (k == 0) {
-            bufA[0] = make_float2(0.0f, 0.0f);
-            bufA[half] = make_float2(x.x, y.x);            // Nyquist: real parts only
-        } else {
-            bufA[k] = make_float2(x.x - y.y, x.y + y.x);
-            bufA[N - k] = make_float2(x.x + y.y, y.x - x.y);
+    for (int h = 0; h < 2; ++h) {
+        float2 x[8], sth[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tt + ((h * 8 + e) << log2T);
+            const int slot = (h == 0) ? idx : ((N - idx) & (half - 1));     // idx = N/2 -> 0
+            x[e] = __ldg(rowU + slot);
+            sth[e] = __ldg(rowS + slot);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tt + ((h * 8 + e) << log2T);
+            const float2 y = make_float2(sth[e].x - x[e].x, sth[e].y - x[e].y);
+            if (h == 0) v[e] = (idx == 0) ? make_float2(0.0f, 0.0f) : make_float2(x[e].x - y.y, x[e].y + y.x);
+            else v[8 + e] = (idx == half) ? make_float2(x[e].x, y.x) : make_float2(x[e].x + y.y, y.x - x[e].y);
         }
     }
-    __syncthreads();
-    const float2* z = fftShared<+1>(bufA, bufB, N, g.log2NPhi, tid, t.twiddle);
+    fftFromRegisters<+1>(v, buf, tt, T, N, g.log2NPhi, tw, twReady);
 
-    const float denomPhi = __ldg(t.gradPhiDenom + j);
-    const float negH = -g.h;
-    float* pressure = pressureAll ? pressureAll + (size_t)sim * g.cells : nullptr;
+    // v[m] = z[i], i = tt + m*T: z.x = p[j][i], z.y = p[j+1][i] - p[j][i]
+    if (!valid) return;
+    // gradient subtraction (applyPressurePhi / applyPressureTheta, kernel/KaminoCore.cu:716-746);
+    // the projection is compared with the reference to fp32 round-off, not bit for bit, so the
+    // two divisions by row constants become multiplications by their reciprocals
+    const float invDenomPhi = 1.0f / __ldg(t.gradPhiDenom + j);
+    const float invNegH = -1.0f / g.h;
+    float* pressure = pressureAll ? pressureAll + (size_t)sim * g.cells + (size_t)j * N : nullptr;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = tid + r * (N >> 2);
-        const float2 zi = z[i];
-        const float pWest = z[(i - 1) & (N - 1)].x;
-        // applyPressurePhi, kernel/KaminoCore.cu:740-746
-        const size_t at = (size_t)j * N + i;
-        velPhi[at] = __fadd_rn(velPhi[at], __fdiv_rn(__fsub_rn(zi.x, pWest), denomPhi));
-        // applyPressureTheta, kernel/KaminoCore.cu:716-721 (zi.y = p[j+1][i] - p[j][i])
-        if (hasSouth) velTheta[at] = __fadd_rn(velTheta[at], __fdiv_rn(zi.y, negH));
-        if (pressure) pressure[at] = zi.x;
+    for (int h = 0; h < 2; ++h) {
+        float uOld[8], vOld[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int i = tt + ((h * 8 + m) << log2T);
+            uOld[m] = velPhi[i];
+            vOld[m] = hasSouth ? velTheta[i] : 0.0f;
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int i = tt + ((h * 8 + m) << log2T);
+            const float2 zi = v[h * 8 + m];
+            const float pWest = buf[fft::pad((i - 1) & (N - 1))].x;
+            velPhi[i] = __fmaf_rn(__fsub_rn(zi.x, pWest), invDenomPhi, uOld[m]);
+            if (hasSouth) velTheta[i] = __fmaf_rn(zi.y, invNegH, vOld[m]);
+            if (pressure) pressure[i] = zi.x;
+        }
     }
-}
-
-int tridiagonalWidth(const GridParams& g)
-{
-    // W systems per block: W * nTheta/2 threads <= 1024, W <= 4 (32-byte row segments)
-    int W = 2048 / g.nTheta;
-    if (W > 4) W = 4;
-    if (W < 1) W = 1;
-    while ((g.nPhi / 2) % W) W >>= 1;
-    return W;
-}
-
-size_t tridiagonalSmem(const GridParams& g, int W)
-{
-    const int L = g.nTheta + (g.nTheta >> 5) + 1;
-    return (size_t)W * 7 * L * sizeof(float);
 }
 
 } // namespace
 
 size_t spectralTableBytes(const GridParams& g)
 {
-    return sizeof(float2) * g.nPhi + sizeof(float) * 7 * g.nTheta + 256 * 8;
+    return sizeof(float2) * g.nPhi + sizeof(float) * 8 * g.nTheta + sizeof(float) * crTableFloats(g) + 256 * 13;
 }
 
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream)
@@ -371,46 +310,81 @@ cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_
     return cudaGetLastError();
 }
 
+namespace {
+
+// FFT launch geometry: T = N/16 threads per transform, blocks of max(T, 64) threads; the
+// twiddle table is staged in shared memory up to N = 4096 (32 KB)
+struct FftLaunch { int block; int perBlock; bool stage; size_t smem; };
+FftLaunch fftLaunch(const GridParams& g)
+{
+    const int T = g.nPhi >> 4;
+    FftLaunch l;
+    l.block = T < 64 ? 64 : T;
+    l.perBlock = l.block / T;
+    l.stage = g.nPhi <= 4096 && g.nPhi >= 64;
+    l.smem = ((size_t)l.perBlock * fft::paddedSize(g.nPhi) + (l.stage ? g.nPhi : 0)) * sizeof(float2);
+    return l;
+}
+
+template <int BLOCK, bool STAGE>
+cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
+                        const float* velPhiIn, const float* velThetaIn, float2* spectrum,
+                        float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream)
+{
+    if (which == 0) {           // configure
+        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+    }
+    if (which == 1) {
+        const int pairs = g.nTheta / 2;
+        dim3 grid((pairs + l.perBlock - 1) / l.perBlock, batch);
+        divergenceFFTKernel<BLOCK, STAGE><<<grid, BLOCK, l.smem, stream>>>(g, t, velPhiIn, velThetaIn, spectrum);
+    } else {
+        dim3 grid((g.nTheta + l.perBlock - 1) / l.perBlock, batch);
+        inverseFFTGradientKernel<BLOCK, STAGE><<<grid, BLOCK, l.smem, stream>>>(g, t, spectrum, velPhi, velTheta, pressure);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, const float* velPhiIn,
+                      const float* velThetaIn, float2* spectrum, float* velPhi, float* velTheta,
+                      float* pressure, int batch, cudaStream_t stream)
+{
+    const FftLaunch l = fftLaunch(g);
+#define KB_FFT(B, S) return fftDispatch<B, S>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream)
+    switch (l.block) {
+    case 64: if (l.stage) KB_FFT(64, true); else KB_FFT(64, false);
+    case 128: KB_FFT(128, true);
+    case 256: KB_FFT(256, true);
+    case 512: KB_FFT(512, false);
+    case 1024: KB_FFT(1024, false);
+    default: return cudaErrorInvalidValue;
+    }
+#undef KB_FFT
+}
+
+} // namespace
+
 cudaError_t configureKernels(const GridParams& g)
 {
-    cudaError_t e;
-    const size_t fftSmem = 2 * (size_t)g.nPhi * sizeof(float2);
-    e = cudaFuncSetAttribute(divergenceFFTKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fftSmem);
+    SpectralTables none{};
+    cudaError_t e = fftSelect(0, g, none, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, nullptr);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(inverseFFTGradientKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fftSmem);
-    if (e != cudaSuccess) return e;
-    const int W = tridiagonalWidth(g);
-    e = cudaFuncSetAttribute(tridiagonalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tridiagonalSmem(g, W));
-    return e;
+    return configureTridiagonal(g);
 }
 
 cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, const float* velPhi,
                                 const float* velTheta, float2* spectrum, int batch, cudaStream_t stream)
 {
-    dim3 grid(g.nTheta / 2, batch);
-    divergenceFFTKernel<<<grid, g.nPhi / 4, 2 * (size_t)g.nPhi * sizeof(float2), stream>>>(
-        g, t, velPhi, velTheta, spectrum);
-    return cudaGetLastError();
-}
-
-cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
-                              cudaStream_t stream)
-{
-    const int W = tridiagonalWidth(g);
-    dim3 grid((g.nPhi / 2) / W, batch);
-    tridiagonalKernel<<<grid, W * (g.nTheta / 2), tridiagonalSmem(g, W), stream>>>(g, t, spectrum, W);
-    return cudaGetLastError();
+    return fftSelect(1, g, t, velPhi, velTheta, spectrum, nullptr, nullptr, nullptr, batch, stream);
 }
 
 cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
                                      float* velPhi, float* velTheta, float* pressure, int batch,
                                      cudaStream_t stream)
 {
-    dim3 grid(g.nTheta, batch);
-    inverseFFTGradientKernel<<<grid, g.nPhi / 4, 2 * (size_t)g.nPhi * sizeof(float2), stream>>>(
-        g, t, spectrum, velPhi, velTheta, pressure);
-    return cudaGetLastError();
+    return fftSelect(2, g, t, nullptr, nullptr, const_cast<float2*>(spectrum), velPhi, velTheta, pressure, batch, stream);
 }
 
 } // namespace kb
