@@ -23,9 +23,9 @@ constexpr int kAdvectThreads = 256;
 //  * 0.5 * (mu + gu) is an fp32 add followed by an exact halving;
 //  * g - aver*cof is one FFMA in the reference's SASS.
 template <int KIND>
-__device__ __forceinline__ float backtrace(const GridParams& g, const float* __restrict__ velPhi,
+__device__ __forceinline__ float backtrace(const SamplerRegs& g, float cofTheta, const float* __restrict__ velPhi,
                                            const float* __restrict__ velTheta,
-                                           const float* __restrict__ src, int i, int j)
+                                           const float* __restrict__ src, int i, int j, float cofPhi)
 {
     const float offPhi = (KIND == kVPhi) ? -0.5f : 0.0f;
     const float offTheta = (KIND == kVTheta) ? 1.0f : 0.5f;
@@ -35,9 +35,7 @@ __device__ __forceinline__ float backtrace(const GridParams& g, const float* __r
     const float guPhi = sample<kVPhi>(g, velPhi, gPhi, gTheta);
     const float guTheta = sample<kVTheta>(g, velTheta, gPhi, gTheta);
 
-    const float latRadius = __fmul_rn(g.radius, sinf(gTheta));
-    const float cofPhi = __fdiv_rn(g.dt, latRadius);
-    const float cofTheta = g.cofTheta;
+    // cofPhi = dt / (R sinf(gTheta)) depends on the row only: tabulated (same device functions)
 
     const float deltaPhi = __fmul_rn(guPhi, cofPhi);
     const float deltaTheta = __fmul_rn(guTheta, cofTheta);
@@ -57,59 +55,63 @@ __device__ __forceinline__ float backtrace(const GridParams& g, const float* __r
 }
 
 // kernel/KaminoCore.cu:321-342
-__device__ __forceinline__ float2 pushParticle(const GridParams& g, const float* __restrict__ velPhi,
+__device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, float radius, float dt, float cofTheta,
+                                               const float* __restrict__ velPhi,
                                                const float* __restrict__ velTheta, float2 pos)
 {
     const float posPhi = pos.x, posTheta = pos.y;
     const float uPhi = sample<kVPhi>(g, velPhi, posPhi, posTheta);
     const float uTheta = sample<kVTheta>(g, velTheta, posPhi, posTheta);
-    const float latRadius = __fmul_rn(g.radius, sinf(posTheta));
-    const float cofPhi = __fdiv_rn(g.dt, latRadius);
-    float updatedTheta = __fmaf_rn(uTheta, g.cofTheta, posTheta);
+    const float latRadius = __fmul_rn(radius, sinf(posTheta));
+    const float cofPhi = __fdiv_rn(dt, latRadius);
+    float updatedTheta = __fmaf_rn(uTheta, cofTheta, posTheta);
     float updatedPhi = posPhi;
     if (latRadius > 1e-7f) updatedPhi = __fmaf_rn(uPhi, cofPhi, posPhi);
-    validateCoord(updatedPhi, updatedTheta);
+    if (!(__float_as_uint(updatedTheta) < 0x40490FDBu && __float_as_uint(updatedPhi) < 0x40C90FDBu)) {
+        const Validated v = validateCoord(updatedPhi, updatedTheta);
+        updatedPhi = v.phi; updatedTheta = v.theta;
+    }
     return make_float2(updatedPhi, updatedTheta);
 }
+
+// Grid: [tile blocks | particle blocks] x batch. A tile block owns kTileRows x 32 cells (one warp
+// per row segment, so stores stay 128-byte coalesced) and runs the u_phi, u_theta and density
+// backtraces of its cells one after the other: the three kinds gather from the same
+// neighbourhood of velPhi / velTheta, so the second and third pass hit in L1, and the velocity
+// is streamed from HBM once per step instead of once per kind.
+constexpr int kTileRows = kAdvectThreads / 32;
 
 __global__ void __launch_bounds__(kAdvectThreads)
 advectKernel(GridParams g, AdvectArgs a)
 {
     const int sim = blockIdx.y;
-    const float* velPhi = a.velPhi + (size_t)sim * g.cells;
-    const float* velTheta = a.velTheta + (size_t)sim * g.cells;
-    const int N = g.nPhi;
-    int block = blockIdx.x;
+    const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
+    const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
+    const SamplerRegs sr(g);
+    const int block = blockIdx.x;
 
-    if (block < a.blocksPhi) {
-        const int cell = block * kAdvectThreads + threadIdx.x;
-        const int j = cell >> g.log2NPhi, i = cell & (N - 1);
-        a.velPhiOut[(size_t)sim * g.cells + cell] = backtrace<kVPhi>(g, velPhi, velTheta, velPhi, i, j);
+    if (block < a.tileBlocks) {
+        const int log2TilesX = g.log2NPhi - 5;
+        const int i = ((block & ((1 << log2TilesX) - 1)) << 5) + (threadIdx.x & 31);
+        const int j = (block >> log2TilesX) * kTileRows + (threadIdx.x >> 5);
+        const size_t cell = (size_t)sim * g.cells + (size_t)j * g.nPhi + i;
+        if (a.parts & kAdvectVelocity) {
+            a.velPhiOut[cell] = backtrace<kVPhi>(sr, g.cofTheta, velPhi, velTheta, velPhi, i, j, __ldg(a.cofPhiCentred + j));
+            if (j < g.nTheta - 1)
+                a.velThetaOut[cell] = backtrace<kVTheta>(sr, g.cofTheta, velPhi, velTheta, velTheta, i, j, __ldg(a.cofPhiTheta + j));
+        }
+        if ((a.parts & kAdvectScalars) && a.density) {
+            const float* density = pinPointer(a.density + (size_t)sim * g.cells);
+            a.densityOut[cell] = backtrace<kCentered>(sr, g.cofTheta, velPhi, velTheta, density, i, j, __ldg(a.cofPhiCentred + j));
+        }
         return;
     }
-    block -= a.blocksPhi;
-    if (block < a.blocksTheta) {
-        const int cell = block * kAdvectThreads + threadIdx.x;
-        const int j = cell >> g.log2NPhi, i = cell & (N - 1);
-        if (j < g.nTheta - 1)
-            a.velThetaOut[(size_t)sim * g.cells + cell] = backtrace<kVTheta>(g, velPhi, velTheta, velTheta, i, j);
-        return;
-    }
-    block -= a.blocksTheta;
-    if (block < a.blocksDensity) {
-        const int cell = block * kAdvectThreads + threadIdx.x;
-        const int j = cell >> g.log2NPhi, i = cell & (N - 1);
-        const float* density = a.density + (size_t)sim * g.cells;
-        a.densityOut[(size_t)sim * g.cells + cell] = backtrace<kCentered>(g, velPhi, velTheta, density, i, j);
-        return;
-    }
-    block -= a.blocksDensity;
     {
-        const long k = (long)block * kAdvectThreads + threadIdx.x;
+        const long k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
         if (k < g.numParticles) {                       // the reference has no tail guard (:323)
             const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
             float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
-            out[k] = pushParticle(g, velPhi, velTheta, in[k]);
+            out[k] = pushParticle(sr, g.radius, g.dt, g.cofTheta, velPhi, velTheta, in[k]);
         }
     }
 }
@@ -121,27 +123,29 @@ __global__ void locateKernel(GridParams g, long n, const float* __restrict__ phi
 {
     long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    Location loc = locate<KIND>(g, phiRaw[k], thetaRaw[k]);
+    const SamplerRegs sr(g);
+    Location loc = locate<KIND>(sr, phiRaw[k], thetaRaw[k]);
     phiIndex[k] = loc.phiIndex;
     thetaIndex[k] = loc.thetaIndex;
     alphaPhi[k] = loc.alphaPhi;
     alphaTheta[k] = loc.alphaTheta;
     phiOut[k] = loc.phi;
     thetaOut[k] = loc.theta;
-    flags[k] = (loc.flipped ? 1 : 0) | (poleBranch<KIND>(g, loc) ? 2 : 0);
+    flags[k] = (loc.flipped ? 1 : 0) | (poleBranch<KIND>(sr, loc) ? 2 : 0);
 }
 
 } // namespace
 
-cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
+cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int parts, int batch, cudaStream_t stream)
 {
-    const int cellBlocks = (int)(g.cells / kAdvectThreads);
-    a.blocksPhi = cellBlocks;
-    a.blocksTheta = cellBlocks;
-    a.blocksDensity = a.density ? cellBlocks : 0;
-    const int blocksParticles = (a.particles && g.numParticles > 0)
+    const bool velocity = (parts & kAdvectVelocity) != 0, scalars = (parts & kAdvectScalars) != 0;
+    a.parts = parts;
+    a.tileBlocks = (velocity || (scalars && a.density)) ? (g.nPhi / 32) * (g.nTheta / kTileRows) : 0;
+    const int blocksParticles = (scalars && a.particles && g.numParticles > 0)
         ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
-    dim3 grid(a.blocksPhi + a.blocksTheta + a.blocksDensity + blocksParticles, batch);
+    const int blocks = a.tileBlocks + blocksParticles;
+    if (blocks == 0) return cudaSuccess;
+    dim3 grid(blocks, batch);
     advectKernel<<<grid, kAdvectThreads, 0, stream>>>(g, a);
     return cudaGetLastError();
 }

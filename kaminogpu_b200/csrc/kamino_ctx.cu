@@ -116,7 +116,9 @@ cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
     a.velThetaOut = ctx->velTheta[st.vel ^ 1];
     a.densityOut = ctx->density[st.density ^ 1];
     a.particlesOut = ctx->g.numParticles > 0 ? ctx->particles[st.particle ^ 1] : nullptr;
-    cudaError_t e = launchAdvect(ctx->g, a, ctx->batch, s);
+    a.cofPhiCentred = ctx->tables.cofPhiCentred;
+    a.cofPhiTheta = ctx->tables.cofPhiTheta;
+    cudaError_t e = launchAdvect(ctx->g, a, kAdvectAll, ctx->batch, s);
     st.vel ^= 1; st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
     return e;
 }
@@ -320,6 +322,8 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         ctx->tables.triC = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.sinSq = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.geoG = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.cofPhiCentred = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.cofPhiTheta = (float*)sub(sizeof(float) * nTheta);
         const size_t slotRows = (size_t)nTheta * (g.nPhi / 2);
         ctx->tables.crFwd = (float2*)sub(sizeof(float2) * slotRows);
         ctx->tables.crA = (float*)sub(sizeof(float) * slotRows);

@@ -15,10 +15,16 @@ struct AdvectArgs {
     float* velThetaOut;
     float* densityOut;
     float* particlesOut;
-    int blocksPhi, blocksTheta, blocksDensity;   // filled by launchAdvect
+    // per-row dt / (R sinf(theta_node)) of the u_phi / density nodes and of the u_theta nodes
+    const float* cofPhiCentred;
+    const float* cofPhiTheta;
+    int parts, tileBlocks;                       // filled by launchAdvect
 };
 
-cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
+// which parts of the advection one launch covers (bit mask)
+enum AdvectParts { kAdvectVelocity = 1, kAdvectScalars = 2, kAdvectAll = 3 };
+
+cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int parts, int batch, cudaStream_t stream);
 
 cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phiRaw, const float* thetaRaw,
                          int* phiIndex, int* thetaIndex, float* alphaPhi, float* alphaTheta,
@@ -36,6 +42,8 @@ struct SpectralTables {
     float* triC;          // nTheta: super-diagonal               (:137-138)
     float* sinSq;         // nTheta: sinf(theta_j)^2              (:134)
     float* geoG;          // nTheta: dt*cosf(theta_j)/(R*sinf(theta_j))   (kernel/KaminoCore.cu:494)
+    float* cofPhiCentred; // nTheta: dt/(R*sinf((j+1/2)h))  cofPhi of u_phi / density nodes (:202-203, :292-293)
+    float* cofPhiTheta;   // nTheta: dt/(R*sinf((j+1)h))    cofPhi of u_theta nodes (:247-248)
     double minusTwoOverH2;  // -2.0 / (h*h)                        (:133)
     // cyclic-reduction factors of every wavenumber slot (tridiag.cu), layout [.][slot]
     float2* crFwd;        // nTheta x N/2: (tmp1, tmp2) of forward level l, element idx at row nTheta-(nTheta>>l)+idx

@@ -42,8 +42,10 @@ __device__ __forceinline__ float wrapTwoPi(float x)
     return (float)(xd - (double)k * kTwoPi);
 }
 
-// kernel/KaminoCore.cu:11-29; returns true when the reference returns -1.
-__device__ __forceinline__ bool validateCoord(float& phi, float& theta)
+// kernel/KaminoCore.cu:11-29; `flipped` is true when the reference returns -1.
+struct Validated { float phi, theta; bool flipped; };
+
+__device__ __forceinline__ Validated validateCoordInline(float phi, float theta)
 {
     bool flipped = false;
     theta = wrapTwoPi(theta);
@@ -58,7 +60,14 @@ __device__ __forceinline__ bool validateCoord(float& phi, float& theta)
         flipped = !flipped;
     }
     phi = wrapTwoPi(phi);
-    return flipped;
+    return Validated{phi, theta, flipped};
+}
+
+// Out of line (values in registers both ways): only lanes that cross a pole or the seam come
+// here, the callers test the in-range case first.
+__device__ __noinline__ Validated validateCoord(float phi, float theta)
+{
+    return validateCoordInline(phi, theta);
 }
 
 // kernel/KaminoCore.cu:31-34
@@ -73,18 +82,45 @@ __device__ __forceinline__ float lerpFast(float from, float to, float alpha, flo
     return __fmaf_rn(oneMinusAlpha, from, __fmul_rn(alpha, to));
 }
 
+// Grid constants held in registers for the whole kernel (the opaque moves keep the compiler
+// from re-loading them from the constant bank at every use: the kernel is issue-bound).
+struct SamplerRegs {
+    float h, halfH, invH;
+    int N, mask, halfN, nTheta;
+    __device__ __forceinline__ explicit SamplerRegs(const GridParams& g)
+    {
+        h = g.h; halfH = g.halfH; invH = g.invH;
+        N = g.nPhi; mask = g.nPhi - 1; halfN = g.nPhi >> 1; nTheta = g.nTheta;
+        asm volatile("" : "+f"(h), "+f"(halfH), "+f"(invH));
+        asm volatile("" : "+r"(N), "+r"(mask), "+r"(halfN), "+r"(nTheta));
+    }
+};
+
+// keep a base pointer in a register pair so that element `idx` is one IMAD.WIDE away
+__device__ __forceinline__ const float* pinPointer(const float* p)
+{
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
+// Index / weight / predicate part of the samplers (kernel/KaminoCore.cu:36-53, 86-103, 136-153).
 template <int KIND>
-__device__ __forceinline__ Location locate(const GridParams& g, float phiRaw, float thetaRaw)
+__device__ __forceinline__ Location locate(const SamplerRegs& g, float phiRaw, float thetaRaw)
 {
     Location loc;
     // stagger shift (kernel/KaminoCore.cu:38-39, 88-89, 138-139)
     float phi = (KIND == kVPhi) ? __fadd_rn(phiRaw, g.halfH) : phiRaw;
     float theta = (KIND == kVTheta) ? __fsub_rn(thetaRaw, g.h) : __fsub_rn(thetaRaw, g.halfH);
-    loc.flipped = validateCoord(phi, theta);
-    float normedPhi = __fmul_rn(phi, g.invH);
-    float normedTheta = __fmul_rn(theta, g.invH);
+    // in range (0 <= theta < pi and 0 <= phi < 2 pi) validateCoord is the identity
+    loc.flipped = false;
+    if (!(__float_as_uint(theta) < 0x40490FDBu && __float_as_uint(phi) < 0x40C90FDBu)) {
+        const Validated v = validateCoord(phi, theta);
+        phi = v.phi; theta = v.theta; loc.flipped = v.flipped;
+    }
+    const float normedPhi = __fmul_rn(phi, g.invH);
+    const float normedTheta = __fmul_rn(theta, g.invH);
     loc.phiIndex = (int)floorf(normedPhi);
-    loc.thetaIndex = (int)floorf(normedTheta);
+    loc.thetaIndex = (int)floorf(normedTheta);       // >= 0: theta >= 0 after validateCoord
     loc.alphaPhi = __fsub_rn(normedPhi, (float)loc.phiIndex);
     loc.alphaTheta = __fsub_rn(normedTheta, (float)loc.thetaIndex);
     loc.phi = phi;
@@ -92,59 +128,63 @@ __device__ __forceinline__ Location locate(const GridParams& g, float phiRaw, fl
     return loc;
 }
 
+// pole branch of the reference (:52-53, :102-103, :152-153)
 template <int KIND>
-__device__ __forceinline__ bool poleBranch(const GridParams& g, const Location& loc)
+__device__ __forceinline__ bool poleBranch(const SamplerRegs& g, const Location& loc)
 {
-    const int poleRow = (KIND == kVTheta) ? g.nTheta - 2 : g.nTheta - 1;
-    return (loc.thetaIndex == 0 && loc.flipped) || loc.thetaIndex == poleRow;
+    const int lastRow = (KIND == kVTheta) ? g.nTheta - 2 : g.nTheta - 1;
+    return (loc.thetaIndex == lastRow) || (loc.thetaIndex == 0 && loc.flipped);
 }
 
 // One bilinear sample of `field` (rows x nPhi, dense) at the raw coordinate.
+//
+// Instruction diet (the advection kernel is issue-bound, profiles/r01c): the in-range case
+// (0 <= theta < pi, 0 <= phi < 2 pi, true for every lane that does not cross a pole or the
+// seam) is detected with two unsigned compares on the bit patterns (-0.0f and NaN fall
+// through to validateCoord, which treats them as the reference does); all four gathers are
+// addressed with 32-bit element offsets from one base pointer; the pole / out-of-range row
+// handling is two selects.
 template <int KIND>
-__device__ __forceinline__ float sample(const GridParams& g, const float* __restrict__ field,
+__device__ __forceinline__ float sample(const SamplerRegs& g, const float* __restrict__ field,
                                         float phiRaw, float thetaRaw)
 {
     const Location loc = locate<KIND>(g, phiRaw, thetaRaw);
-    const int N = g.nPhi;
-    const int rows = (KIND == kVTheta) ? g.nTheta - 1 : g.nTheta;
-    const int phiLower = loc.phiIndex & (N - 1);          // size_t % nPhi, nPhi = 2^k
-    const int phiHigher = (phiLower + 1) & (N - 1);
-    const bool pole = poleBranch<KIND>(g, loc);
-
-    // Rows outside the array are clamped: the reference reads out of bounds there
-    // (undefined; only reachable when the theta-CFL exceeds 1 at the south pole).
-    const int rowLo = min(max(loc.thetaIndex, 0), rows - 1);
-    int colA, colB, rowHi;
-    if (pole) {
-        // single-row branch: second belt is the same row at phi + pi
-        rowHi = rowLo;
-        colA = (phiLower + (N >> 1)) & (N - 1);
-        colB = (colA + 1) & (N - 1);
-    } else {
-        rowHi = min(rowLo + 1, rows - 1);
-        colA = phiLower;
-        colB = phiHigher;
-    }
-    const float* lo = field + (size_t)rowLo * N;
-    const float* hi = field + (size_t)rowHi * N;
-    const float v00 = __ldg(lo + phiLower);
-    const float v01 = __ldg(lo + phiHigher);
-    const float v10 = __ldg(hi + colA);
-    const float v11 = __ldg(hi + colB);
-
+    const int phiIndex = loc.phiIndex, thetaIndex = loc.thetaIndex;
+    const float alphaPhi = loc.alphaPhi;
     float alphaTheta = loc.alphaTheta;
-    if (pole && KIND != kVPhi) alphaTheta = __fmul_rn(0.5f, alphaTheta);   // :115, :165
+    const int N = g.N, mask = g.mask;
+    const int lastRow = (KIND == kVTheta) ? g.nTheta - 2 : g.nTheta - 1;
+    const bool pole = poleBranch<KIND>(g, loc);
+    // rows past the array are clamped to the last one: the reference reads out of bounds
+    // there (undefined; only reachable when the theta-CFL exceeds 1 at the south pole)
+    const bool oneRow = pole || thetaIndex > lastRow;
+    const int rowLo = min(thetaIndex, lastRow);
+    const int colShift = pole ? g.halfN : 0;             // second belt = same row at phi + pi
+    const int rowStep = oneRow ? 0 : N;
+    const int c0 = phiIndex & mask;                         // size_t % nPhi, nPhi = 2^k
+    const int c1 = (c0 + 1) & mask;
+    const int cA = (c0 + colShift) & mask;
+    const int cB = (cA + 1) & mask;
+    const int lo = rowLo * N;
+    const int hi = lo + rowStep;
+    const float v00 = __ldg(field + (lo + c0));
+    const float v01 = __ldg(field + (lo + c1));
+    const float v10 = __ldg(field + (hi + cA));
+    const float v11 = __ldg(field + (hi + cB));
 
-    const float omPhi = __fsub_rn(1.0f, loc.alphaPhi);
-    const float omTheta = __fsub_rn(1.0f, alphaTheta);
-    const bool exact = (__fsub_rn(1.0f, omPhi) == loc.alphaPhi) && (__fsub_rn(1.0f, omTheta) == alphaTheta);
-    if (exact) {
-        const float lowerBelt = lerpFast(v00, v01, loc.alphaPhi, omPhi);
-        const float higherBelt = lerpFast(v10, v11, loc.alphaPhi, omPhi);
+    if (KIND != kVPhi) alphaTheta = pole ? __fmul_rn(0.5f, alphaTheta) : alphaTheta;   // :115, :165
+
+    // alpha is a multiple of 2^-23 (2^-24 after the halving) whenever the index is >= 1, which
+    // makes 1 - alpha exact in fp32 (see the file header)
+    if (min(phiIndex, thetaIndex) >= 1) {
+        const float omPhi = __fsub_rn(1.0f, alphaPhi);
+        const float omTheta = __fsub_rn(1.0f, alphaTheta);
+        const float lowerBelt = lerpFast(v00, v01, alphaPhi, omPhi);
+        const float higherBelt = lerpFast(v10, v11, alphaPhi, omPhi);
         return lerpFast(lowerBelt, higherBelt, alphaTheta, omTheta);
     } else {
-        const float lowerBelt = lerpWide(v00, v01, loc.alphaPhi);
-        const float higherBelt = lerpWide(v10, v11, loc.alphaPhi);
+        const float lowerBelt = lerpWide(v00, v01, alphaPhi);
+        const float higherBelt = lerpWide(v10, v11, alphaPhi);
         return lerpWide(lowerBelt, higherBelt, alphaTheta);
     }
 }

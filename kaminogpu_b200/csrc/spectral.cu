@@ -90,6 +90,10 @@ __global__ void buildTablesKernel(GridParams g, SpectralTables t)
         t.sinSq[k] = __fmul_rn(sinT, sinT);
         // geometricFillKernel, kernel/KaminoCore.cu:494
         t.geoG[k] = __fdiv_rn(__fmul_rn(g.dt, cosT), __fmul_rn(g.radius, sinT));
+        // advection kernels, kernel/KaminoCore.cu:196,202-203 / 241,247-248 / 286,292-293
+        t.cofPhiCentred[k] = __fdiv_rn(g.dt, __fmul_rn(g.radius, sinT));
+        const float thetaV = __fmul_rn(__fadd_rn((float)k, 1.0f), h);
+        t.cofPhiTheta[k] = __fdiv_rn(g.dt, __fmul_rn(g.radius, sinf(thetaV)));
     }
 }
 
@@ -299,7 +303,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 
 size_t spectralTableBytes(const GridParams& g)
 {
-    return sizeof(float2) * g.nPhi + sizeof(float) * 8 * g.nTheta + sizeof(float) * crTableFloats(g) + 256 * 13;
+    return sizeof(float2) * g.nPhi + sizeof(float) * 10 * g.nTheta + sizeof(float) * crTableFloats(g) + 256 * 15;
 }
 
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream)
