@@ -5,63 +5,81 @@
 // launches and two device syncs become ONE launch whose 1-D grid is partitioned into
 // four block ranges (u_phi cells | u_theta cells | density cells | particles). All four
 // read the pre-advection velocity, as in the reference.
+#include <cstdlib>
+#include <cstring>
+
 #include "kamino_kernels.cuh"
 #include "sampler.cuh"
 
 namespace kb {
 
+namespace { thread_local bool g_capturing = false; }
+
+void pdlSetCapturing(bool capturing) { g_capturing = capturing; }
+
+bool pdlEnabled()
+{
+    static const bool on = [] { const char* e = getenv("KAMINO_PDL"); return e ? atoi(e) != 0 : true; }();
+    return on && g_capturing;
+}
+
 namespace {
 
 constexpr int kAdvectThreads = 256;
 
-// One RK2 backtrace from the node of `KIND` cell (j, i); samples `src` at the foot point.
-// kernel/KaminoCore.cu:195-228 (and :240-273, :285-318). Arithmetic notes:
-//  * node coordinate ((fReal)i + offset) * gridLen is an exact fp64 sum and product
-//    rounded once, which equals the fp32 product of the exact fp32 sum;
-//  * g - 0.5*delta (fp64 in the reference) is an exact product and a sum of two fp32
-//    values, i.e. fmaf(-0.5, delta, g);
-//  * 0.5 * (mu + gu) is an fp32 add followed by an exact halving;
-//  * g - aver*cof is one FFMA in the reference's SASS.
+// One RK2 backtrace from the node of `KIND` cell (j, i); samples `src` at the foot point. The
+// two velocity samples of each stage are issued together. kernel/KaminoCore.cu:195-228
+// (and :240-273, :285-318); arithmetic notes below.
 template <int KIND>
-__device__ __forceinline__ float backtrace(const SamplerRegs& g, float cofTheta, const float* __restrict__ velPhi,
-                                           const float* __restrict__ velTheta,
+__device__ __forceinline__ float backtrace(const SamplerRegs& g, const SamplerConsts* __restrict__ sc, float cofTheta,
+                                           const float* __restrict__ velPhi, const float* __restrict__ velTheta,
                                            const float* __restrict__ src, int i, int j, float cofPhi)
 {
     const float offPhi = (KIND == kVPhi) ? -0.5f : 0.0f;
     const float offTheta = (KIND == kVTheta) ? 1.0f : 0.5f;
     const float gPhi = __fmul_rn(__fadd_rn((float)i, offPhi), g.h);
     const float gTheta = __fmul_rn(__fadd_rn((float)j, offTheta), g.h);
-
-    const float guPhi = sample<kVPhi>(g, velPhi, gPhi, gTheta);
-    const float guTheta = sample<kVTheta>(g, velTheta, gPhi, gTheta);
-
-    // cofPhi = dt / (R sinf(gTheta)) depends on the row only: tabulated (same device functions)
-
+    PendingSample pu = sampleIssue<kVPhi>(g, sc, velPhi, gPhi, gTheta);
+    PendingSample pv = sampleIssue<kVTheta>(g, sc, velTheta, gPhi, gTheta);
+    const float guPhi = sampleFinish(pu);
+    const float guTheta = sampleFinish(pv);
     const float deltaPhi = __fmul_rn(guPhi, cofPhi);
     const float deltaTheta = __fmul_rn(guTheta, cofTheta);
-
     const float midPhi = __fmaf_rn(-0.5f, deltaPhi, gPhi);
     const float midTheta = __fmaf_rn(-0.5f, deltaTheta, gTheta);
-    const float muPhi = sample<kVPhi>(g, velPhi, midPhi, midTheta);
-    const float muTheta = sample<kVTheta>(g, velTheta, midPhi, midTheta);
-
+    pu = sampleIssue<kVPhi>(g, sc, velPhi, midPhi, midTheta);
+    pv = sampleIssue<kVTheta>(g, sc, velTheta, midPhi, midTheta);
+    const float muPhi = sampleFinish(pu);
+    const float muTheta = sampleFinish(pv);
     const float averuPhi = __fmul_rn(0.5f, __fadd_rn(muPhi, guPhi));
     const float averuTheta = __fmul_rn(0.5f, __fadd_rn(muTheta, guTheta));
-
     const float pPhi = __fmaf_rn(-averuPhi, cofPhi, gPhi);
     const float pTheta = __fmaf_rn(-averuTheta, cofTheta, gTheta);
-
-    return sample<KIND>(g, src, pPhi, pTheta);
+    return sample<KIND>(g, sc, src, pPhi, pTheta);
 }
 
+// Arithmetic notes for backtrace():
+//  * node coordinate ((fReal)i + offset) * gridLen is an exact fp64 sum and product
+//    rounded once, which equals the fp32 product of the exact fp32 sum;
+//  * g - 0.5*delta (fp64 in the reference) is an exact product and a sum of two fp32
+//    values, i.e. fmaf(-0.5, delta, g);
+//  * 0.5 * (mu + gu) is an fp32 add followed by an exact halving;
+//  * g - aver*cof is one FFMA in the reference's SASS;
+//  * cofPhi = dt / (R sinf(gTheta)) depends on the row only: tabulated (same device functions).
+// Tried and rejected (r01g/r01h A/B): advancing the three backtraces of a cell stage by stage so
+// that six samples are in flight per round -- 80-100 registers, 10 % slower than this form.
+
 // kernel/KaminoCore.cu:321-342
-__device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, float radius, float dt, float cofTheta,
+__device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, const SamplerConsts* __restrict__ sc,
+                                               float radius, float dt, float cofTheta,
                                                const float* __restrict__ velPhi,
                                                const float* __restrict__ velTheta, float2 pos)
 {
     const float posPhi = pos.x, posTheta = pos.y;
-    const float uPhi = sample<kVPhi>(g, velPhi, posPhi, posTheta);
-    const float uTheta = sample<kVTheta>(g, velTheta, posPhi, posTheta);
+    const PendingSample pu = sampleIssue<kVPhi>(g, sc, velPhi, posPhi, posTheta);
+    const PendingSample pv = sampleIssue<kVTheta>(g, sc, velTheta, posPhi, posTheta);
+    const float uPhi = sampleFinish(pu);
+    const float uTheta = sampleFinish(pv);
     const float latRadius = __fmul_rn(radius, sinf(posTheta));
     const float cofPhi = __fdiv_rn(dt, latRadius);
     float updatedTheta = __fmaf_rn(uTheta, cofTheta, posTheta);
@@ -78,52 +96,51 @@ __device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, float radiu
 // per row segment, so stores stay 128-byte coalesced) and runs the u_phi, u_theta and density
 // backtraces of its cells one after the other: the three kinds gather from the same
 // neighbourhood of velPhi / velTheta, so the second and third pass hit in L1, and the velocity
-// is streamed from HBM once per step instead of once per kind.
+// is streamed from HBM once per step instead of once per kind. The particle blocks (one
+// thread per particle) come last in the grid and fill the tail of the tile blocks.
 constexpr int kTileRows = kAdvectThreads / 32;
 
-__global__ void __launch_bounds__(kAdvectThreads)
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(kAdvectThreads, MINBLOCKS)
 advectKernel(GridParams g, AdvectArgs a)
 {
     const int sim = blockIdx.y;
     const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
     const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
-    const SamplerRegs sr(g);
+    const SamplerRegs sr(a.consts);            // read-only table: independent of the previous kernel
     const int block = blockIdx.x;
+    pdlWait();
 
     if (block < a.tileBlocks) {
+        const float* density = pinPointer(a.density + (size_t)sim * g.cells);
         const int log2TilesX = g.log2NPhi - 5;
         const int i = ((block & ((1 << log2TilesX) - 1)) << 5) + (threadIdx.x & 31);
         const int j = (block >> log2TilesX) * kTileRows + (threadIdx.x >> 5);
         const size_t cell = (size_t)sim * g.cells + (size_t)j * g.nPhi + i;
-        if (a.parts & kAdvectVelocity) {
-            a.velPhiOut[cell] = backtrace<kVPhi>(sr, g.cofTheta, velPhi, velTheta, velPhi, i, j, __ldg(a.cofPhiCentred + j));
-            if (j < g.nTheta - 1)
-                a.velThetaOut[cell] = backtrace<kVTheta>(sr, g.cofTheta, velPhi, velTheta, velTheta, i, j, __ldg(a.cofPhiTheta + j));
-        }
-        if ((a.parts & kAdvectScalars) && a.density) {
-            const float* density = pinPointer(a.density + (size_t)sim * g.cells);
-            a.densityOut[cell] = backtrace<kCentered>(sr, g.cofTheta, velPhi, velTheta, density, i, j, __ldg(a.cofPhiCentred + j));
-        }
+        const float cofCentred = __ldg(a.cofPhiCentred + j);
+        a.velPhiOut[cell] = backtrace<kVPhi>(sr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred);
+        if (j < g.nTheta - 1)
+            a.velThetaOut[cell] = backtrace<kVTheta>(sr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
+                                                     __ldg(a.cofPhiTheta + j));
+        a.densityOut[cell] = backtrace<kCentered>(sr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j, cofCentred);
         return;
     }
-    {
-        const long k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
-        if (k < g.numParticles) {                       // the reference has no tail guard (:323)
-            const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
-            float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
-            out[k] = pushParticle(sr, g.radius, g.dt, g.cofTheta, velPhi, velTheta, in[k]);
-        }
+    const long k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
+    if (k < g.numParticles) {                       // the reference has no tail guard (:323)
+        const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
+        float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
+        out[k] = pushParticle(sr, a.consts, g.radius, g.dt, g.cofTheta, velPhi, velTheta, in[k]);
     }
 }
 
 template <int KIND>
-__global__ void locateKernel(GridParams g, long n, const float* __restrict__ phiRaw,
+__global__ void locateKernel(const SamplerConsts* __restrict__ consts, long n, const float* __restrict__ phiRaw,
                              const float* __restrict__ thetaRaw, int* phiIndex, int* thetaIndex,
                              float* alphaPhi, float* alphaTheta, float* phiOut, float* thetaOut, int* flags)
 {
     long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const SamplerRegs sr(g);
+    const SamplerRegs sr(consts);
     Location loc = locate<KIND>(sr, phiRaw[k], thetaRaw[k]);
     phiIndex[k] = loc.phiIndex;
     thetaIndex[k] = loc.thetaIndex;
@@ -136,21 +153,42 @@ __global__ void locateKernel(GridParams g, long n, const float* __restrict__ phi
 
 } // namespace
 
-cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int parts, int batch, cudaStream_t stream)
+void fillSamplerConsts(const GridParams& g, void* hostBlock64)
 {
-    const bool velocity = (parts & kAdvectVelocity) != 0, scalars = (parts & kAdvectScalars) != 0;
-    a.parts = parts;
-    a.tileBlocks = (velocity || (scalars && a.density)) ? (g.nPhi / 32) * (g.nTheta / kTileRows) : 0;
-    const int blocksParticles = (scalars && a.particles && g.numParticles > 0)
-        ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
-    const int blocks = a.tileBlocks + blocksParticles;
-    if (blocks == 0) return cudaSuccess;
-    dim3 grid(blocks, batch);
-    advectKernel<<<grid, kAdvectThreads, 0, stream>>>(g, a);
-    return cudaGetLastError();
+    SamplerConsts c{};
+    c.h = g.h; c.halfH = g.halfH; c.invH = g.invH;
+    c.N = g.nPhi; c.mask = g.nPhi - 1; c.halfN = g.nPhi >> 1; c.nTheta = g.nTheta;
+    auto bits = [](float x) { unsigned u; memcpy(&u, &x, 4); return u; };
+    // interior fast path of sample(): see sampler.cuh. lastRow = nTheta-1 (u_phi, centred) / nTheta-2 (u_theta)
+    const float lo = 1.5f * g.h;
+    const float hiCentred = ((float)(g.nTheta - 1) - 0.5f) * g.h;
+    const float hiVTheta = ((float)(g.nTheta - 2) - 0.5f) * g.h;
+    c.thetaLoBits = bits(lo);
+    c.thetaSpanCentred = bits(hiCentred) - bits(lo);
+    c.thetaSpanVTheta = bits(hiVTheta) - bits(lo);
+    c.phiLoBits = bits(lo);
+    c.phiSpan = bits(kTwoPiF) - bits(lo);
+    static_assert(sizeof(SamplerConsts) == 64, "SamplerConsts is a 64-byte block");
+    memcpy(hostBlock64, &c, sizeof(c));
 }
 
-cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phiRaw, const float* thetaRaw,
+cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
+{
+    // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget), default 5
+    static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 5; }();
+    a.tileBlocks = (g.nPhi / 32) * (g.nTheta / kTileRows);
+    const int blocksParticles = (a.particles && g.numParticles > 0)
+        ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
+    dim3 grid(a.tileBlocks + blocksParticles, batch);
+    switch (variant) {
+    case 3: return launchChained(advectKernel<3>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    case 4: return launchChained(advectKernel<4>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    case 6: return launchChained(advectKernel<6>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    default: return launchChained(advectKernel<5>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    }
+}
+
+cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const float* phiRaw, const float* thetaRaw,
                          int* phiIndex, int* thetaIndex, float* alphaPhi, float* alphaTheta,
                          float* phiOut, float* thetaOut, int* flags, cudaStream_t stream)
 {
@@ -159,15 +197,15 @@ cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phi
     if (blocks == 0) return cudaSuccess;
     switch (kind) {
     case kVPhi:
-        locateKernel<kVPhi><<<blocks, threads, 0, stream>>>(g, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
+        locateKernel<kVPhi><<<blocks, threads, 0, stream>>>(consts, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
                                                             alphaPhi, alphaTheta, phiOut, thetaOut, flags);
         break;
     case kVTheta:
-        locateKernel<kVTheta><<<blocks, threads, 0, stream>>>(g, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
+        locateKernel<kVTheta><<<blocks, threads, 0, stream>>>(consts, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
                                                               alphaPhi, alphaTheta, phiOut, thetaOut, flags);
         break;
     default:
-        locateKernel<kCentered><<<blocks, threads, 0, stream>>>(g, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
+        locateKernel<kCentered><<<blocks, threads, 0, stream>>>(consts, n, phiRaw, thetaRaw, phiIndex, thetaIndex,
                                                                 alphaPhi, alphaTheta, phiOut, thetaOut, flags);
         break;
     }

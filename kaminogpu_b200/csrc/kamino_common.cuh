@@ -40,6 +40,38 @@ struct FieldSet {
     const float* density;
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The five kernels of a step form a chain in which every kernel consumes what the previous one
+// wrote. Inside a captured step graph they are launched with the programmatic-stream-
+// serialization attribute: the launch of kernel k+1 is set up while kernel k drains (its blocks
+// become schedulable when every block of kernel k has exited or is exiting), and every kernel
+// calls pdlWait() before its first dependent global access (read OR write), which blocks until
+// kernel k has completed and its writes are visible, so the chain stays transitively ordered.
+// Stream capture turns the attribute into programmatic graph edges.
+// Measured (r01j A/B): triggering the dependents EARLY (griddepcontrol.launch_dependents at
+// kernel entry) is a large loss -- the waiting blocks of kernel k+1 take SM slots from the
+// later waves of kernel k -- so no kernel triggers explicitly. Outside graph capture (phase
+// entry points, which may follow a memcpy) launches are plain. KAMINO_PDL=0/1 switches it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdlEnabled();
+void pdlSetCapturing(bool capturing);   // set by the context around graph capture
+
+template <typename... KArgs, typename... Args>
+cudaError_t launchChained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdlEnabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define KB_CUDA_OK(expr)                                                     \
     do {                                                                     \
         cudaError_t kb_err__ = (expr);                                       \

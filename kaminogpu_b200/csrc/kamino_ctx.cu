@@ -118,7 +118,8 @@ cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
     a.particlesOut = ctx->g.numParticles > 0 ? ctx->particles[st.particle ^ 1] : nullptr;
     a.cofPhiCentred = ctx->tables.cofPhiCentred;
     a.cofPhiTheta = ctx->tables.cofPhiTheta;
-    cudaError_t e = launchAdvect(ctx->g, a, kAdvectAll, ctx->batch, s);
+    a.consts = ctx->tables.samplerConsts;
+    cudaError_t e = launchAdvect(ctx->g, a, ctx->batch, s);
     st.vel ^= 1; st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
     return e;
 }
@@ -192,7 +193,9 @@ int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
     cudaGraph_t graph = nullptr;
     KB_TRY(ctx, cudaStreamBeginCapture(ctx->ownStream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
+    pdlSetCapturing(true);
     for (int k = 0; k < steps && e == cudaSuccess; ++k) e = enqueueStep(ctx, st, ctx->ownStream);
+    pdlSetCapturing(false);
     cudaError_t e2 = cudaStreamEndCapture(ctx->ownStream, &graph);
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(ctx, (int)e, "graph capture (launch)"); }
     if (e2 != cudaSuccess) return fail(ctx, (int)e2, "cudaStreamEndCapture");
@@ -324,6 +327,7 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         ctx->tables.geoG = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.cofPhiCentred = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.cofPhiTheta = (float*)sub(sizeof(float) * nTheta);
+        ctx->tables.samplerConsts = (SamplerConsts*)sub(64);
         const size_t slotRows = (size_t)nTheta * (g.nPhi / 2);
         ctx->tables.crFwd = (float2*)sub(sizeof(float2) * slotRows);
         ctx->tables.crA = (float*)sub(sizeof(float) * slotRows);
@@ -339,6 +343,12 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         && cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming) == cudaSuccess;
     ctx->stream = ctx->ownStream;
     if (ok) ok = configureKernels(g) == cudaSuccess;
+    if (ok) {
+        char block[64];
+        fillSamplerConsts(g, block);
+        ok = cudaMemcpyAsync(ctx->tables.samplerConsts, block, sizeof(block), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess
+            && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    }
     if (ok) ok = launchBuildTables(g, ctx->tables, ctx->stream) == cudaSuccess;
     if (ok) ok = launchBuildCrTables(g, ctx->tables, ctx->stream) == cudaSuccess;
     if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
@@ -615,7 +625,7 @@ int kamino_debug_locate(kamino_ctx* ctx, int kind, long n, const float* phiRaw, 
     cudaStream_t s = ctx->stream;
     cudaError_t e = cudaMemcpyAsync(dPhi, phiRaw, sizeof(float) * n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dTheta, thetaRaw, sizeof(float) * n, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = launchLocate(ctx->g, kind, n, dPhi, dTheta, dPi, dTi, dAp, dAt, dPv, dTv, dFl, s);
+    if (e == cudaSuccess) e = launchLocate(ctx->tables.samplerConsts, kind, n, dPhi, dTheta, dPi, dTi, dAp, dAt, dPv, dTv, dFl, s);
     auto back = [&](void* host, const void* dev) {
         if (e == cudaSuccess && host) e = cudaMemcpyAsync(host, dev, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
     };

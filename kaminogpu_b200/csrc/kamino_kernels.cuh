@@ -6,6 +6,8 @@
 
 namespace kb {
 
+struct SamplerConsts;
+
 struct AdvectArgs {
     const float* velPhi;       // this-step buffers (whole batch)
     const float* velTheta;
@@ -18,15 +20,14 @@ struct AdvectArgs {
     // per-row dt / (R sinf(theta_node)) of the u_phi / density nodes and of the u_theta nodes
     const float* cofPhiCentred;
     const float* cofPhiTheta;
-    int parts, tileBlocks;                       // filled by launchAdvect
+    const SamplerConsts* consts;  // device copy of the sampler constants (sampler.cuh)
+    int tileBlocks;                              // filled by launchAdvect
 };
 
-// which parts of the advection one launch covers (bit mask)
-enum AdvectParts { kAdvectVelocity = 1, kAdvectScalars = 2, kAdvectAll = 3 };
+cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
 
-cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int parts, int batch, cudaStream_t stream);
-
-cudaError_t launchLocate(const GridParams& g, int kind, long n, const float* phiRaw, const float* thetaRaw,
+struct SamplerConsts;
+cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const float* phiRaw, const float* thetaRaw,
                          int* phiIndex, int* thetaIndex, float* alphaPhi, float* alphaTheta,
                          float* phiOut, float* thetaOut, int* flags, cudaStream_t stream);
 
@@ -44,6 +45,7 @@ struct SpectralTables {
     float* geoG;          // nTheta: dt*cosf(theta_j)/(R*sinf(theta_j))   (kernel/KaminoCore.cu:494)
     float* cofPhiCentred; // nTheta: dt/(R*sinf((j+1/2)h))  cofPhi of u_phi / density nodes (:202-203, :292-293)
     float* cofPhiTheta;   // nTheta: dt/(R*sinf((j+1)h))    cofPhi of u_theta nodes (:247-248)
+    SamplerConsts* samplerConsts;  // 64 bytes, filled by fillSamplerConsts + a host-to-device copy
     double minusTwoOverH2;  // -2.0 / (h*h)                        (:133)
     // cyclic-reduction factors of every wavenumber slot (tridiag.cu), layout [.][slot]
     float2* crFwd;        // nTheta x N/2: (tmp1, tmp2) of forward level l, element idx at row nTheta-(nTheta>>l)+idx
@@ -74,6 +76,9 @@ cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, floa
 cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
                                      float* velPhi, float* velTheta, float* pressure, int batch,
                                      cudaStream_t stream);
+
+// host: the constants block of the samplers for this grid
+void fillSamplerConsts(const GridParams& g, void* hostBlock64);
 
 // One-time setup of kernel attributes (opt-in shared memory); called at context creation.
 cudaError_t configureKernels(const GridParams& g);

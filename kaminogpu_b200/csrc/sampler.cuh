@@ -82,17 +82,34 @@ __device__ __forceinline__ float lerpFast(float from, float to, float alpha, flo
     return __fmaf_rn(oneMinusAlpha, from, __fmul_rn(alpha, to));
 }
 
-// Grid constants held in registers for the whole kernel (the opaque moves keep the compiler
-// from re-loading them from the constant bank at every use: the kernel is issue-bound).
+// Grid constants held in registers for the whole kernel. They are LOADED from a small global
+// table (SamplerConsts, built by the host at context creation) rather than read from the kernel
+// parameters: ptxas re-materialises parameter reads from the constant bank at every use (6 extra
+// LDC/LDCU per sample in the r01e profile of this issue-bound kernel), but it never re-issues a
+// global load.
+struct SamplerConsts {               // 16 words, 16-byte aligned
+    float h, halfH, invH, pad0;
+    int N, mask, halfN, nTheta;
+    // interior fast path: shifted theta in [thetaLo, thetaHi[kind]) and shifted phi in [phiLo, 2 pi)
+    // as unsigned ranges on the bit patterns: (bits - lo) < span
+    unsigned thetaLoBits, thetaSpanCentred, thetaSpanVTheta, pad1;
+    unsigned phiLoBits, phiSpan, pad2, pad3;
+};
+
 struct SamplerRegs {
     float h, halfH, invH;
     int N, mask, halfN, nTheta;
-    __device__ __forceinline__ explicit SamplerRegs(const GridParams& g)
+    unsigned thetaLoBits, thetaSpanCentred, thetaSpanVTheta, phiLoBits, phiSpan;
+    __device__ __forceinline__ explicit SamplerRegs(const SamplerConsts* __restrict__ c)
     {
-        h = g.h; halfH = g.halfH; invH = g.invH;
-        N = g.nPhi; mask = g.nPhi - 1; halfN = g.nPhi >> 1; nTheta = g.nTheta;
-        asm volatile("" : "+f"(h), "+f"(halfH), "+f"(invH));
-        asm volatile("" : "+r"(N), "+r"(mask), "+r"(halfN), "+r"(nTheta));
+        const float4 a = __ldg(reinterpret_cast<const float4*>(c));
+        const int4 b = __ldg(reinterpret_cast<const int4*>(c) + 1);
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(c) + 2);
+        const uint4 e = __ldg(reinterpret_cast<const uint4*>(c) + 3);
+        h = a.x; halfH = a.y; invH = a.z;
+        N = b.x; mask = b.y; halfN = b.z; nTheta = b.w;
+        thetaLoBits = d.x; thetaSpanCentred = d.y; thetaSpanVTheta = d.z;
+        phiLoBits = e.x; phiSpan = e.y;
     }
 };
 
@@ -136,17 +153,15 @@ __device__ __forceinline__ bool poleBranch(const SamplerRegs& g, const Location&
     return (loc.thetaIndex == lastRow) || (loc.thetaIndex == 0 && loc.flipped);
 }
 
-// One bilinear sample of `field` (rows x nPhi, dense) at the raw coordinate.
-//
-// Instruction diet (the advection kernel is issue-bound, profiles/r01c): the in-range case
-// (0 <= theta < pi, 0 <= phi < 2 pi, true for every lane that does not cross a pole or the
-// seam) is detected with two unsigned compares on the bit patterns (-0.0f and NaN fall
-// through to validateCoord, which treats them as the reference does); all four gathers are
-// addressed with 32-bit element offsets from one base pointer; the pole / out-of-range row
-// handling is two selects.
+// One bilinear sample of `field` (rows x nPhi, dense) at the raw coordinate: the general path
+// (pole and seam crossings, first row / column, last rows). All four gathers are addressed with
+// 32-bit element offsets from one base pointer; the pole / out-of-range row handling is two
+// selects; the in-range case of validateCoord is detected with two unsigned compares on the
+// bit patterns (-0.0f and NaN fall through to validateCoord, which treats them as the
+// reference does).
 template <int KIND>
-__device__ __forceinline__ float sample(const SamplerRegs& g, const float* __restrict__ field,
-                                        float phiRaw, float thetaRaw)
+__device__ __forceinline__ float sampleGeneralInline(const SamplerRegs& g, const float* __restrict__ field,
+                                                     float phiRaw, float thetaRaw)
 {
     const Location loc = locate<KIND>(g, phiRaw, thetaRaw);
     const int phiIndex = loc.phiIndex, thetaIndex = loc.thetaIndex;
@@ -187,6 +202,79 @@ __device__ __forceinline__ float sample(const SamplerRegs& g, const float* __res
         const float higherBelt = lerpWide(v10, v11, alphaPhi);
         return lerpWide(lowerBelt, higherBelt, alphaTheta);
     }
+}
+
+// Out-of-line instance of the general path; it re-loads the constants it needs (cold code).
+template <int KIND>
+__device__ __noinline__ float sampleGeneral(const SamplerConsts* __restrict__ consts, const float* __restrict__ field,
+                                            float phiRaw, float thetaRaw)
+{
+    const SamplerRegs g(consts);
+    return sampleGeneralInline<KIND>(g, field, phiRaw, thetaRaw);
+}
+
+// The sample as the kernels call it, split in two so that the gathers of several independent
+// samples are in flight together (the kernel is otherwise bound by one exposed memory latency
+// per sample): sampleIssue() computes the cell and issues the four loads, sampleFinish() does
+// the three lerps.
+//
+// Interior fast path: when the shifted coordinate satisfies
+//   1.5 h <= theta < (lastRow - 0.5) h   and   1.5 h <= phi < 2 pi
+// then validateCoord is the identity, 1 <= thetaIndex < lastRow (no pole branch, no clamping),
+// phiIndex >= 1, and both weights are multiples of 2^-23, so 1 - alpha is exact in fp32 and
+// the three lerps are FMUL + FFMA (file header). Everything else takes the general path, out of
+// line, and its finished value v travels through sampleFinish() as the degenerate bilinear
+// form (v, v, v, v; alpha = 0), which returns v unchanged (1*v + 0*v, exact for finite v).
+// Both paths evaluate the reference's expressions, so which one a lane takes never changes a bit.
+struct PendingSample { float v00, v01, v10, v11, alphaPhi, alphaTheta; };
+
+template <int KIND>
+__device__ __forceinline__ PendingSample sampleIssue(const SamplerRegs& g, const SamplerConsts* __restrict__ consts,
+                                                     const float* __restrict__ field, float phiRaw, float thetaRaw)
+{
+    const float phi = (KIND == kVPhi) ? __fadd_rn(phiRaw, g.halfH) : phiRaw;
+    const float theta = (KIND == kVTheta) ? __fsub_rn(thetaRaw, g.h) : __fsub_rn(thetaRaw, g.halfH);
+    const unsigned thetaSpan = (KIND == kVTheta) ? g.thetaSpanVTheta : g.thetaSpanCentred;
+    const bool interior = (__float_as_uint(theta) - g.thetaLoBits) < thetaSpan
+                       && (__float_as_uint(phi) - g.phiLoBits) < g.phiSpan;
+    PendingSample p;
+    if (interior) {
+        const float normedPhi = __fmul_rn(phi, g.invH);
+        const float normedTheta = __fmul_rn(theta, g.invH);
+        const int phiIndex = (int)floorf(normedPhi);
+        const int thetaIndex = (int)floorf(normedTheta);
+        p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
+        p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
+        const int c0 = phiIndex & g.mask;
+        const int c1 = (c0 + 1) & g.mask;
+        const int lo0 = thetaIndex * g.N + c0;
+        const int lo1 = thetaIndex * g.N + c1;
+        p.v00 = __ldg(field + lo0);
+        p.v01 = __ldg(field + lo1);
+        p.v10 = __ldg(field + (lo0 + g.N));
+        p.v11 = __ldg(field + (lo1 + g.N));
+    } else {
+        const float v = sampleGeneral<KIND>(consts, field, phiRaw, thetaRaw);
+        p.v00 = p.v01 = p.v10 = p.v11 = v;
+        p.alphaPhi = p.alphaTheta = 0.0f;
+    }
+    return p;
+}
+
+__device__ __forceinline__ float sampleFinish(const PendingSample& p)
+{
+    const float omPhi = __fsub_rn(1.0f, p.alphaPhi);
+    const float omTheta = __fsub_rn(1.0f, p.alphaTheta);
+    const float lowerBelt = lerpFast(p.v00, p.v01, p.alphaPhi, omPhi);
+    const float higherBelt = lerpFast(p.v10, p.v11, p.alphaPhi, omPhi);
+    return lerpFast(lowerBelt, higherBelt, p.alphaTheta, omTheta);
+}
+
+template <int KIND>
+__device__ __forceinline__ float sample(const SamplerRegs& g, const SamplerConsts* __restrict__ consts,
+                                        const float* __restrict__ field, float phiRaw, float thetaRaw)
+{
+    return sampleFinish(sampleIssue<KIND>(g, consts, field, phiRaw, thetaRaw));
 }
 
 } // namespace kb

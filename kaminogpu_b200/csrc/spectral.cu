@@ -158,6 +158,7 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
 
     uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, N);
     const float2* tw = STAGE ? twShared : t.twiddle;
+    pdlWait();                                   // the velocity comes from the previous kernel
 
     // divergence of rows j and j + 1 (fillDivergenceKernel, kernel/KaminoCore.cu:598-632) at the
     // 16 columns i = tt + e*T of this thread; all loads of a half are issued before they are used
@@ -245,6 +246,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 
     uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, N);
     const float2* tw = STAGE ? twShared : t.twiddle;
+    pdlWait();                                   // the spectrum comes from the previous kernel
 
     // W_k = X_k + i Y_k with X = U_j, Y = U_{j+1} - U_j (Hermitian completions), X_0 = Y_0 = 0.
     // Thread tt needs W at idx = tt + e*T: for idx < N/2 from slot idx, for idx > N/2 from the
@@ -303,7 +305,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 
 size_t spectralTableBytes(const GridParams& g)
 {
-    return sizeof(float2) * g.nPhi + sizeof(float) * 10 * g.nTheta + sizeof(float) * crTableFloats(g) + 256 * 15;
+    return sizeof(float2) * g.nPhi + sizeof(float) * 10 * g.nTheta + sizeof(float) * crTableFloats(g) + 256 * 16;
 }
 
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream)
@@ -343,12 +345,12 @@ cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t,
     if (which == 1) {
         const int pairs = g.nTheta / 2;
         dim3 grid((pairs + l.perBlock - 1) / l.perBlock, batch);
-        divergenceFFTKernel<BLOCK, STAGE><<<grid, BLOCK, l.smem, stream>>>(g, t, velPhiIn, velThetaIn, spectrum);
+        return launchChained(divergenceFFTKernel<BLOCK, STAGE>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum);
     } else {
         dim3 grid((g.nTheta + l.perBlock - 1) / l.perBlock, batch);
-        inverseFFTGradientKernel<BLOCK, STAGE><<<grid, BLOCK, l.smem, stream>>>(g, t, spectrum, velPhi, velTheta, pressure);
+        return launchChained(inverseFFTGradientKernel<BLOCK, STAGE>, grid, dim3(BLOCK), l.smem, stream, g, t,
+                             (const float2*)spectrum, velPhi, velTheta, pressure);
     }
-    return cudaGetLastError();
 }
 
 cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, const float* velPhiIn,

@@ -151,6 +151,7 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
         fwd = sFwd; tabA = sA; tabB = sB; tabC = sC;
     }
 
+    pdlWait();                                   // the right-hand sides come from the previous kernel
     for (int item = tid; item < nT * W; item += THREADS) {
         const int i = item >> LW, w = item & (W - 1);
         d[swizzleRow<W>(i) * W + w] = spectrum[(size_t)i * half + w];
@@ -262,8 +263,7 @@ cudaError_t launchTri(const GridParams& g, const SpectralTables& t, float2* spec
     if (configureOnly)
         return cudaFuncSetAttribute(tridiagonalKernel<W, THREADS, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((g.nPhi / 2) / W, batch);
-    tridiagonalKernel<W, THREADS, STAGE><<<grid, THREADS, smem, stream>>>(g, t, spectrum);
-    return cudaGetLastError();
+    return launchChained(tridiagonalKernel<W, THREADS, STAGE>, grid, dim3(THREADS), smem, stream, g, t, spectrum);
 }
 
 cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
