@@ -33,29 +33,30 @@ constexpr int kAdvectThreads = 256;
 template <int KIND>
 __device__ __forceinline__ float backtrace(const SamplerRegs& g, const SamplerConsts* __restrict__ sc, float cofTheta,
                                            const float* __restrict__ velPhi, const float* __restrict__ velTheta,
-                                           const float* __restrict__ src, int i, int j, float cofPhi)
+                                           const float* __restrict__ src, int i, int j, float cofPhi,
+                                           const float* tilePhi, const float* tileTheta, const float* tileSrc)
 {
     const float offPhi = (KIND == kVPhi) ? -0.5f : 0.0f;
     const float offTheta = (KIND == kVTheta) ? 1.0f : 0.5f;
     const float gPhi = __fmul_rn(__fadd_rn((float)i, offPhi), g.h);
     const float gTheta = __fmul_rn(__fadd_rn((float)j, offTheta), g.h);
-    PendingSample pu = sampleIssue<kVPhi>(g, sc, velPhi, gPhi, gTheta);
-    PendingSample pv = sampleIssue<kVTheta>(g, sc, velTheta, gPhi, gTheta);
+    PendingSample pu = sampleIssue<kVPhi, true>(g, sc, velPhi, gPhi, gTheta, tilePhi);
+    PendingSample pv = sampleIssue<kVTheta, true>(g, sc, velTheta, gPhi, gTheta, tileTheta);
     const float guPhi = sampleFinish(pu);
     const float guTheta = sampleFinish(pv);
     const float deltaPhi = __fmul_rn(guPhi, cofPhi);
     const float deltaTheta = __fmul_rn(guTheta, cofTheta);
     const float midPhi = __fmaf_rn(-0.5f, deltaPhi, gPhi);
     const float midTheta = __fmaf_rn(-0.5f, deltaTheta, gTheta);
-    pu = sampleIssue<kVPhi>(g, sc, velPhi, midPhi, midTheta);
-    pv = sampleIssue<kVTheta>(g, sc, velTheta, midPhi, midTheta);
+    pu = sampleIssue<kVPhi, true>(g, sc, velPhi, midPhi, midTheta, tilePhi);
+    pv = sampleIssue<kVTheta, true>(g, sc, velTheta, midPhi, midTheta, tileTheta);
     const float muPhi = sampleFinish(pu);
     const float muTheta = sampleFinish(pv);
     const float averuPhi = __fmul_rn(0.5f, __fadd_rn(muPhi, guPhi));
     const float averuTheta = __fmul_rn(0.5f, __fadd_rn(muTheta, guTheta));
     const float pPhi = __fmaf_rn(-averuPhi, cofPhi, gPhi);
     const float pTheta = __fmaf_rn(-averuTheta, cofTheta, gTheta);
-    return sample<KIND>(g, sc, src, pPhi, pTheta);
+    return sampleFinish(sampleIssue<KIND, true>(g, sc, src, pPhi, pTheta, tileSrc));
 }
 
 // Arithmetic notes for backtrace():
@@ -93,10 +94,11 @@ __device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, const Sampl
 }
 
 // Grid: [tile blocks | particle blocks] x batch. A tile block owns kTileRows x 32 cells (one warp
-// per row segment, so stores stay 128-byte coalesced) and runs the u_phi, u_theta and density
-// backtraces of its cells one after the other: the three kinds gather from the same
-// neighbourhood of velPhi / velTheta, so the second and third pass hit in L1, and the velocity
-// is streamed from HBM once per step instead of once per kind. The particle blocks (one
+// per row segment, so stores stay 128-byte coalesced), stages the 13 x 40 neighbourhood of
+// u_phi, u_theta and density in shared memory and runs the three backtraces of its cells one
+// after the other: nearly all of their 15 samples per cell are served from the tiles, the rest
+// (polar rows, where the phi displacement exceeds the halo) gather from L1/L2, and every field
+// is streamed from HBM once per step. The particle blocks (one
 // thread per particle) come last in the grid and fill the tail of the tile blocks.
 constexpr int kTileRows = kAdvectThreads / 32;
 
@@ -112,17 +114,37 @@ advectKernel(GridParams g, AdvectArgs a)
     pdlWait();
 
     if (block < a.tileBlocks) {
+        __shared__ float tiles[3][kTileH * kTileW];
         const float* density = pinPointer(a.density + (size_t)sim * g.cells);
         const int log2TilesX = g.log2NPhi - 5;
-        const int i = ((block & ((1 << log2TilesX) - 1)) << 5) + (threadIdx.x & 31);
-        const int j = (block >> log2TilesX) * kTileRows + (threadIdx.x >> 5);
+        const int i0 = (block & ((1 << log2TilesX) - 1)) << 5;
+        const int j0 = (block >> log2TilesX) * kTileRows;
+        SamplerRegs tr = sr;
+        tr.tileRow0 = j0 - 2;
+        tr.tileCol0 = i0 - 4;
+        // stage the neighbourhood of the block's cells (rows clamped into the arrays: clamped rows
+        // are never addressed by an interior sample; columns wrap around the seam)
+        for (int e = threadIdx.x; e < kTileH * kTileW; e += kAdvectThreads) {
+            const int r = e / kTileW, c = e - r * kTileW;
+            const int col = (tr.tileCol0 + c) & sr.mask;
+            const int row = min(max(tr.tileRow0 + r, 0), sr.nTheta - 1);
+            const int rowV = min(row, sr.nTheta - 2);
+            tiles[0][e] = __ldg(velPhi + (row * sr.N + col));
+            tiles[1][e] = __ldg(velTheta + (rowV * sr.N + col));
+            tiles[2][e] = __ldg(density + (row * sr.N + col));
+        }
+        __syncthreads();
+        const int i = i0 + (threadIdx.x & 31);
+        const int j = j0 + (threadIdx.x >> 5);
         const size_t cell = (size_t)sim * g.cells + (size_t)j * g.nPhi + i;
         const float cofCentred = __ldg(a.cofPhiCentred + j);
-        a.velPhiOut[cell] = backtrace<kVPhi>(sr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred);
+        a.velPhiOut[cell] = backtrace<kVPhi>(tr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred,
+                                             tiles[0], tiles[1], tiles[0]);
         if (j < g.nTheta - 1)
-            a.velThetaOut[cell] = backtrace<kVTheta>(sr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
-                                                     __ldg(a.cofPhiTheta + j));
-        a.densityOut[cell] = backtrace<kCentered>(sr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j, cofCentred);
+            a.velThetaOut[cell] = backtrace<kVTheta>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
+                                                     __ldg(a.cofPhiTheta + j), tiles[0], tiles[1], tiles[1]);
+        a.densityOut[cell] = backtrace<kCentered>(tr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j, cofCentred,
+                                                  tiles[0], tiles[1], tiles[2]);
         return;
     }
     const long k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
