@@ -6,9 +6,9 @@
 //   pressure                             batch x nTheta x nPhi fp32
 //   spectrum                             batch x nTheta x nPhi/2 float2 (half spectrum)
 //   particles[2]                         batch x numParticles float2, double-buffered
-//   tables                               twiddles + per-row constants + the cyclic-reduction
-//                                        factors of every wavenumber (20 B per cell, read-only)
-// = 36 B/cell of state + 20 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
+//   tables                               twiddles + per-row constants + the LU factors of every
+//                                        wavenumber's theta system (10 B per cell, read-only)
+// = 36 B/cell of state + 10 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
 // SURVEY.md appendix B).
 #include <cstdio>
 #include <cstdlib>
@@ -329,10 +329,12 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         ctx->tables.cofPhiTheta = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.samplerConsts = (SamplerConsts*)sub(64);
         const size_t slotRows = (size_t)nTheta * (g.nPhi / 2);
-        ctx->tables.crFwd = (float2*)sub(sizeof(float2) * slotRows);
-        ctx->tables.crA = (float*)sub(sizeof(float) * slotRows);
-        ctx->tables.crB = (float*)sub(sizeof(float) * slotRows);
-        ctx->tables.crC = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.thL = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.thInvB = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.thBetaInv = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.thH = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.thDelta = (float*)sub(sizeof(float) * slotRows);
+        ctx->tables.thBetaEnd = (float*)sub(sizeof(float) * (size_t)(nTheta / 4) * (g.nPhi / 2));
         ctx->tables.minusTwoOverH2 = -2.0 / (double)(g.h * g.h);
     }
 
@@ -342,7 +344,7 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         && cudaEventCreateWithFlags(&ctx->evSnap, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming) == cudaSuccess;
     ctx->stream = ctx->ownStream;
-    if (ok) ok = configureKernels(g) == cudaSuccess;
+    if (ok) ok = configureKernels(g, batch) == cudaSuccess;
     if (ok) {
         char block[64];
         fillSamplerConsts(g, block);
@@ -350,7 +352,7 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
             && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
     if (ok) ok = launchBuildTables(g, ctx->tables, ctx->stream) == cudaSuccess;
-    if (ok) ok = launchBuildCrTables(g, ctx->tables, ctx->stream) == cudaSuccess;
+    if (ok) ok = launchBuildSolveTables(g, ctx->tables, batch, ctx->stream) == cudaSuccess;
     if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     if (ok) ok = allocParticles(ctx, particlesPerSim) == 0;
     if (!ok) {

@@ -47,11 +47,14 @@ struct SpectralTables {
     float* cofPhiTheta;   // nTheta: dt/(R*sinf((j+1)h))    cofPhi of u_theta nodes (:247-248)
     SamplerConsts* samplerConsts;  // 64 bytes, filled by fillSamplerConsts + a host-to-device copy
     double minusTwoOverH2;  // -2.0 / (h*h)                        (:133)
-    // cyclic-reduction factors of every wavenumber slot (tridiag.cu), layout [.][slot]
-    float2* crFwd;        // nTheta x N/2: (tmp1, tmp2) of forward level l, element idx at row nTheta-(nTheta>>l)+idx
-    float* crA;           // nTheta x N/2: a, b, c of every row after the forward elimination
-    float* crB;
-    float* crC;
+    // LU (Thomas) factors of every wavenumber slot and their chunk products (tridiag.cu),
+    // layout [slot group][row][w]
+    float* thL;           // nTheta x N/2: l_i = a_i / b'_{i-1}
+    float* thInvB;        // 1 / b'_i
+    float* thBetaInv;     // beta_i / b'_i, beta_i = prod_{chunk start..i} (-l)
+    float* thH;           // h_i = c_i / b'_i
+    float* thDelta;       // delta_i = prod_{i..chunk end} (-h)
+    float* thBetaEnd;     // beta at the last row of every chunk, [slot group][chunk][w]
 };
 
 // geometric phase: velPhi/velTheta (this) -> velPhiOut/velThetaOut (next)
@@ -59,10 +62,10 @@ cudaError_t launchGeometric(const GridParams& g, const SpectralTables& t, const 
                             float* velPhiOut, float* velThetaOut, int batch, cudaStream_t stream);
 
 size_t spectralTableBytes(const GridParams& g);
-size_t crTableFloats(const GridParams& g);
-cudaError_t configureTridiagonal(const GridParams& g);
-// runs after launchBuildTables (same stream): cyclic reduction of the coefficients, once
-cudaError_t launchBuildCrTables(const GridParams& g, SpectralTables t, cudaStream_t stream);
+size_t solveTableFloats(const GridParams& g);
+cudaError_t configureTridiagonal(const GridParams& g, int batch);
+// runs after launchBuildTables (same stream): LU factorisation of every wavenumber's system, once
+cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream);
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream);
 
 // spectrum layout: S[sim][j][k], k = 0 .. nPhi/2-1, float2; slot k holds wavenumber
@@ -81,6 +84,6 @@ cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& 
 void fillSamplerConsts(const GridParams& g, void* hostBlock64);
 
 // One-time setup of kernel attributes (opt-in shared memory); called at context creation.
-cudaError_t configureKernels(const GridParams& g);
+cudaError_t configureKernels(const GridParams& g, int batch);
 
 } // namespace kb

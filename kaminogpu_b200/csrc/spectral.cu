@@ -305,7 +305,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 
 size_t spectralTableBytes(const GridParams& g)
 {
-    return sizeof(float2) * g.nPhi + sizeof(float) * 10 * g.nTheta + sizeof(float) * crTableFloats(g) + 256 * 16;
+    return sizeof(float2) * g.nPhi + sizeof(float) * 10 * g.nTheta + sizeof(float) * solveTableFloats(g) + 256 * 18;
 }
 
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream)
@@ -372,12 +372,12 @@ cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, c
 
 } // namespace
 
-cudaError_t configureKernels(const GridParams& g)
+cudaError_t configureKernels(const GridParams& g, int batch)
 {
     SpectralTables none{};
     cudaError_t e = fftSelect(0, g, none, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, nullptr);
     if (e != cudaSuccess) return e;
-    return configureTridiagonal(g);
+    return configureTridiagonal(g, batch);
 }
 
 cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, const float* velPhi,

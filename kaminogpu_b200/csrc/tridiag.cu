@@ -4,301 +4,311 @@
 // per step (kernel/tdm.cu:3-96, kernel/KaminoCore.cu:779-792) and the two transposes around
 // them (shiftFKernel's transposed store, copy2UFourier: kernel/KaminoCore.cu:640-670).
 //
-// The reference runs cyclic reduction (CR) on (a, b, c, d) every step, once for the real
-// and once for the imaginary right-hand side. The (a, b, c) part of that recursion does not
-// depend on the right-hand side, so it is executed ONCE, at context creation, by
-// buildCrTablesKernel -- in the reference's elimination order and with its fp32 operations,
-// so every factor has the bits crKernel would produce -- and stored:
-//   crFwd[e]   = (tmp1, tmp2)   elimination factors of forward level l, element idx,
-//                               e = nTheta - (nTheta >> l) + idx          (tdm.cu:55-56)
-//   crA/B/C[e]                  a, b, c of the rows as the back substitution sees them, in
-//                               the order it visits them (contiguous per level)
-// The per-step kernel then only streams the right-hand sides: 2 FMAs per element and level
-// going down, one FMA chain and one IEEE division per element coming up, real and imaginary
-// parts together, reading and writing the half spectrum in place in its [theta][slot]
-// layout (no transposes). A block owns W consecutive wavenumber slots; the tables are laid
-// out per block, [slot group][row][w], so that the slice a block needs is one contiguous
-// range: for grids up to nTheta = 1024 it is brought into shared memory by four TMA bulk
-// copies issued by one thread while the others load the right-hand sides (one exposed
-// global-memory latency per block instead of one per CR level); for larger grids the levels
-// read it directly with fully coalesced loads.
+// The reference runs cyclic reduction (CR) on (a, b, c, d) every step, once for the real and
+// once for the imaginary right-hand side. CR in fp32 is the least accurate part of its step
+// (at 512 x 1024 its pressure is 1.7e-5 away, in relative L2, from an fp64 solve of the same
+// fp32 coefficients; 1.3e-4 at 2048 x 4096), and its log2(nTheta) barrier-
+// separated levels with halving parallelism are slow. This file solves the same systems --
+// same a, b, c, bit for bit the reference's fp32 coefficients -- with an LU (Thomas)
+// factorisation computed ONCE at context creation in fp64 and applied per step as two
+// first-order linear recurrences,
+//     forward :  y_i = d_i - l_i y_{i-1}
+//     backward:  x_i = y_i / b'_i - h_i x_{i+1},          l_i = a_i / b'_{i-1},  h_i = c_i / b'_i,
+// which are parallelised over P chunks of L rows with precomputed multiplier products
+// (beta_i = prod -l, delta_i = prod -h inside a chunk): each chunk runs its recurrence from a
+// zero carry, one thread per system chains the P chunk carries, and a final pass adds
+// carry x product. Dependent chain: 2 L + 2 P steps instead of 2 nTheta (Thomas) or
+// 2 log2(nTheta) block-wide barriers with strided shared-memory traffic (CR). In fp32 the
+// result is 4.7e-7 from the fp64 solve at 512 x 1024 (36 x closer than the reference's own
+// CR), so the pressure differs from the reference's by the reference's rounding error; the
+// parity tests bound it through the fp64 operator.
 //
-// Shared memory holds the right-hand sides of the W systems as float2 d[sw(i) * W + w]; sw()
-// XOR-swizzles the low bits of the row index so that the power-of-two strides of CR are
-// bank-conflict-free without padding.
+// Layout: the half spectrum is solved in place in its [theta][slot] layout (no transposes).
+// A block owns W consecutive wavenumber slots and P * W threads (thread = chunk p, system w).
+// Tables are [slot group][row][w] so that every access of a warp is a run of W floats.
+#include <cstdlib>
+
 #include "kamino_kernels.cuh"
-#include "tma_bulk.cuh"
 
 namespace kb {
 
 namespace {
 
-// log2(16 / W) low bits of i are XORed with the fold of all higher bit groups
-template <int W>
-__device__ __forceinline__ int swizzleRow(int i)
+// ---- launch geometry ----------------------------------------------------------------------------
+
+struct TriLaunch { int W; int L; int P; size_t smem; };
+
+TriLaunch triLaunch(const GridParams& g, int batch)
 {
-    constexpr int B = (W == 2) ? 3 : (W == 4) ? 2 : 1;
-    const int x = i >> B;
-    int f = 0;
-#pragma unroll
-    for (int s = 0; s < 14; s += B) f ^= (x >> s);
-    return i ^ (f & ((1 << B) - 1));
-}
-
-// ---- setup: CR on the coefficients only, one block per wavenumber slot ---------------------
-// dynamic smem: 3 * nTheta floats
-__global__ void buildCrTablesKernel(GridParams g, SpectralTables t, int W)
-{
-    extern __shared__ float sm[];
-    const int nT = g.nTheta, half = g.nPhi >> 1;
-    float* a = sm;
-    float* b = a + nT;
-    float* c = b + nT;
-    const int slot = blockIdx.x;
-    const int n = (slot == 0) ? half : slot;        // wavenumber of this slot (never 0)
-    // table element (row r) of this slot: [(slot / W) * nT + r] * W + slot % W
-    const size_t tabBase = (size_t)(slot / W) * nT * W + (slot % W);
-    const float nSq = (float)(n * n);
-
-    // precomputeABCKernel, kernel/KaminoSolver.cu:128-153
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-        float valA = t.triA[i], valC = t.triC[i];
-        float valB = (float)(t.minusTwoOverH2 - (double)__fdiv_rn(nSq, t.sinSq[i]));
-        if (i == 0) { valB = __fadd_rn(valB, valA); valA = 0.0f; }
-        if (i == nT - 1) { valB = __fadd_rn(valB, valC); valC = 0.0f; }
-        a[i] = valA; b[i] = valB; c[i] = valC;
-    }
-    // forward elimination of the coefficients, kernel/tdm.cu:43-63
-    int levels = 0;
-    while ((2 << levels) < nT) ++levels;            // log2(nT / 2)
-    int stride = 1;
-    for (int lvl = 0; lvl < levels; ++lvl) {
-        __syncthreads();
-        stride <<= 1;
-        const int delta = stride >> 1;
-        const int count = nT >> (lvl + 1);
-        const int entry0 = nT - (nT >> lvl);
-        // two-phase (read, barrier, write) so that a block smaller than `count` stays correct
-        for (int base = 0; base < count; base += blockDim.x) {
-            const int idx = base + threadIdx.x;
-            float ai = 0.f, bi = 0.f, ci = 0.f, tmp1 = 0.f, tmp2 = 0.f;
-            int i = 0;
-            if (idx < count) {
-                i = stride * idx + stride - 1;
-                const int iLeft = i - delta;
-                int iRight = i + delta;
-                if (iRight >= nT) iRight = nT - 1;
-                tmp1 = __fdiv_rn(a[i], b[iLeft]);
-                tmp2 = __fdiv_rn(c[i], b[iRight]);
-                bi = __fmaf_rn(a[iRight], -tmp2, __fmaf_rn(c[iLeft], -tmp1, b[i]));
-                ai = __fmul_rn(a[iLeft], -tmp1);
-                ci = __fmul_rn(c[iRight], -tmp2);
-            }
-            // rows written at this level (odd multiples of delta, minus one) are never read at
-            // this level (reads touch i +- delta, which are rows of the previous level), so no
-            // barrier is needed between the chunks
-            if (idx < count) {
-                a[i] = ai; b[i] = bi; c[i] = ci;
-                t.crFwd[tabBase + (size_t)(entry0 + idx) * W] = make_float2(tmp1, tmp2);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-        // stored in the order the back substitution visits the rows: row i with
-        // i + 1 = (2*idx + 1) * 2^k is entry nTheta - (nTheta >> k) + idx
-        const int k = __ffs(i + 1) - 1;
-        const int e = nT - (nT >> k) + ((i + 1) >> (k + 1));
-        t.crA[tabBase + (size_t)e * W] = a[i];
-        t.crB[tabBase + (size_t)e * W] = b[i];
-        t.crC[tabBase + (size_t)e * W] = c[i];
-    }
-}
-
-// ---- per step ---------------------------------------------------------------------------------
-// grid ((N/2) / W, batch), THREADS threads, dynamic smem nTheta * W * (8 [+ 20 if STAGE]) bytes
-template <int W, int THREADS, bool STAGE>
-__global__ void __launch_bounds__(THREADS)
-tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll)
-{
-    extern __shared__ __align__(16) float2 d[];
-    __shared__ __align__(8) uint64_t tabBar;
-    const int nT = g.nTheta, half = g.nPhi >> 1;
-    const int slot0 = blockIdx.x * W;
-    float2* spectrum = spectrumAll + (size_t)blockIdx.y * (g.cells >> 1) + slot0;
-    const size_t tabBase = (size_t)blockIdx.x * nT * W;
-    const float2* fwd = t.crFwd + tabBase;
-    const float* tabA = t.crA + tabBase;
-    const float* tabB = t.crB + tabBase;
-    const float* tabC = t.crC + tabBase;
-    const int tid = threadIdx.x;
-    constexpr int LW = (W == 2) ? 1 : (W == 4) ? 2 : 3;
-    if (STAGE) {
-        float2* sFwd = d + nT * W;
-        float* sA = reinterpret_cast<float*>(sFwd + nT * W);
-        float* sB = sA + nT * W;
-        float* sC = sB + nT * W;
-        if (tid == 0) { tma::mbarInit(&tabBar, 1); tma::fenceBarrierInit(); }
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(nT * W * sizeof(float));
-            tma::mbarExpectTx(&tabBar, 5 * bytes);
-            tma::bulkLoad(sFwd, fwd, 2 * bytes, &tabBar);
-            tma::bulkLoad(sA, tabA, bytes, &tabBar);
-            tma::bulkLoad(sB, tabB, bytes, &tabBar);
-            tma::bulkLoad(sC, tabC, bytes, &tabBar);
-        }
-        fwd = sFwd; tabA = sA; tabB = sB; tabC = sC;
-    }
-
-    pdlWait();                                   // the right-hand sides come from the previous kernel
-    for (int item = tid; item < nT * W; item += THREADS) {
-        const int i = item >> LW, w = item & (W - 1);
-        d[swizzleRow<W>(i) * W + w] = spectrum[(size_t)i * half + w];
-    }
-
-    int levels = 0;
-    while ((2 << levels) < nT) ++levels;
-    if (STAGE) tma::mbarWait(&tabBar, 0);
-    // forward elimination of the right-hand sides, kernel/tdm.cu:43-63 (d only)
-    int stride = 1;
-    for (int lvl = 0; lvl < levels; ++lvl) {
-        __syncthreads();
-        stride <<= 1;
-        const int delta = stride >> 1;
-        const int count = (nT >> (lvl + 1)) * W;
-        const float2* f = fwd + (size_t)(nT - (nT >> lvl)) * W;
-        for (int item = tid; item < count; item += THREADS) {
-            const int idx = item >> LW, w = item & (W - 1);
-            const int i = stride * idx + stride - 1;
-            const int iLeft = i - delta;
-            int iRight = i + delta;
-            if (iRight >= nT) iRight = nT - 1;
-            const float2 tm = f[idx * W + w];
-            const int pi = swizzleRow<W>(i) * W + w;
-            const float2 dl = d[swizzleRow<W>(iLeft) * W + w], dr = d[swizzleRow<W>(iRight) * W + w];
-            float2 di = d[pi];
-            di.x = __fmaf_rn(dr.x, -tm.y, __fmaf_rn(dl.x, -tm.x, di.x));
-            di.y = __fmaf_rn(dr.y, -tm.y, __fmaf_rn(dl.y, -tm.x, di.y));
-            d[pi] = di;
-        }
-    }
-    __syncthreads();
-    // 2 x 2 system, kernel/tdm.cu:65-72
-    if (tid < W) {
-        const int w = tid;
-        const int i1 = stride - 1, i2 = 2 * stride - 1;
-        const float b1 = tabB[(nT - 2) * W + w], c1 = tabC[(nT - 2) * W + w];     // row i1
-        const float a2 = tabA[(nT - 1) * W + w], b2 = tabB[(nT - 1) * W + w];     // row i2
-        const int p1 = swizzleRow<W>(i1) * W + w, p2 = swizzleRow<W>(i2) * W + w;
-        const float2 d1 = d[p1], d2 = d[p2];
-        const float det = __fmaf_rn(b2, b1, -__fmul_rn(c1, a2));
-        float2 x1, x2;
-        x1.x = __fdiv_rn(__fmaf_rn(b2, d1.x, -__fmul_rn(c1, d2.x)), det);
-        x1.y = __fdiv_rn(__fmaf_rn(b2, d1.y, -__fmul_rn(c1, d2.y)), det);
-        x2.x = __fdiv_rn(__fmaf_rn(d2.x, b1, -__fmul_rn(d1.x, a2)), det);
-        x2.y = __fdiv_rn(__fmaf_rn(d2.y, b1, -__fmul_rn(d1.y, a2)), det);
-        d[p1] = x1;
-        d[p2] = x2;
-    }
-    // back substitution, kernel/tdm.cu:75-90; the solution overwrites the right-hand side
-    int rows = 2;
-    for (int lvl = 0; lvl < levels; ++lvl) {
-        const int delta = stride >> 1;
-        const int e0 = (nT - (nT >> (levels - 1 - lvl))) * W;      // first table entry of this level
-        __syncthreads();
-        for (int item = tid; item < rows * W; item += THREADS) {
-            const int idx = item >> LW, w = item & (W - 1);
-            const int i = stride * idx + delta - 1;
-            const float ci = tabC[e0 + item], bi = tabB[e0 + item];
-            const int pi = swizzleRow<W>(i) * W + w;
-            const float2 di = d[pi], xp = d[swizzleRow<W>(i + delta) * W + w];
-            float2 x;
-            if (i == delta - 1) {
-                x.x = __fdiv_rn(__fmaf_rn(-ci, xp.x, di.x), bi);
-                x.y = __fdiv_rn(__fmaf_rn(-ci, xp.y, di.y), bi);
-            } else {
-                const float ai = tabA[e0 + item];
-                const float2 xm = d[swizzleRow<W>(i - delta) * W + w];
-                x.x = __fdiv_rn(__fmaf_rn(-ci, xp.x, __fmaf_rn(-ai, xm.x, di.x)), bi);
-                x.y = __fdiv_rn(__fmaf_rn(-ci, xp.y, __fmaf_rn(-ai, xm.y, di.y)), bi);
-            }
-            d[pi] = x;
-        }
-        stride >>= 1;
-        rows <<= 1;
-    }
-    __syncthreads();
-    for (int item = tid; item < nT * W; item += THREADS) {
-        const int i = item >> LW, w = item & (W - 1);
-        spectrum[(size_t)i * half + w] = d[swizzleRow<W>(i) * W + w];
-    }
-}
-
-struct TriLaunch { int W; int threads; bool stage; size_t smem; };
-
-TriLaunch triLaunch(const GridParams& g)
-{
-    const int half = g.nPhi / 2;
+    const int nT = g.nTheta, half = g.nPhi / 2;
     TriLaunch l;
-    l.stage = g.nTheta <= 1024;
-    if (l.stage) {
-        // latency regime: as many blocks as possible, tables staged in shared memory
-        l.W = (half / 4 >= 4 * 148) ? 4 : 2;
-    } else {
-        // throughput regime: widest slot group that still gives every SM a couple of blocks
-        l.W = (half / 8 >= 2 * 148) ? 8 : 4;
-        while (l.W > 2 && (size_t)g.nTheta * l.W * sizeof(float2) > 100 * 1024) l.W >>= 1;
+    l.L = nT <= 64 ? 4 : nT <= 256 ? 8 : nT <= 1024 ? 16 : nT <= 4096 ? 32 : 64;
+    l.P = nT / l.L;
+    // W: as wide as possible (64-byte runs) while the grid still has about one block per SM and
+    // the right-hand sides (nTheta * W float2) fit in shared memory (r01o A/B: W = 4 at 512 x 1024,
+    // W = 8 at 2048 x 4096)
+    l.W = 8;
+    while (l.W > 2 && ((long)(half / l.W) * batch < 128 || (size_t)nT * l.W * sizeof(float2) > 160 * 1024)) l.W >>= 1;
+    while (l.P * l.W > (l.L >= 64 ? 512 : 1024)) l.W >>= 1;
+    if (const char* e = getenv("KAMINO_TRI_W")) {
+        const int w = atoi(e);
+        if ((w == 2 || w == 4 || w == 8) && l.P * w <= (l.L >= 64 ? 512 : 1024) && half % w == 0) l.W = w;
     }
-    const int items = g.nTheta / 2 * l.W;
-    l.threads = items >= 1024 ? 512 : (items >= 256 ? 256 : 64);
-    l.smem = (size_t)g.nTheta * l.W * (sizeof(float2) + (l.stage ? 5 * sizeof(float) : 0));
+    l.smem = ((size_t)l.P * (l.L * l.W + l.W) + 2 * (size_t)(l.P + 1) * l.W) * sizeof(float2)
+           + 2 * (size_t)l.P * l.W * sizeof(float);
     return l;
 }
 
-template <int W, int THREADS, bool STAGE>
-cudaError_t launchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, size_t smem,
+// ---- setup: LU factors and chunk products, one thread per wavenumber slot, fp64 -------------------
+
+__global__ void buildSolveTablesKernel(GridParams g, SpectralTables t, int W, int L)
+{
+    const int nT = g.nTheta, half = g.nPhi >> 1;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= half) return;
+    const int n = (slot == 0) ? half : slot;        // wavenumber of this slot (never 0)
+    const size_t base = (size_t)(slot / W) * nT * W + (slot % W);
+    const float nSq = (float)(n * n);
+    const int P = nT / L;
+
+    // forward: l_i, 1/b'_i, h_i and beta_i = prod_{m = chunk start .. i} (-l_m) (from the ROUNDED l)
+    double bPrev = 1.0, cPrev = 0.0, beta = 1.0;
+    for (int i = 0; i < nT; ++i) {
+        // coefficients exactly as precomputeABCKernel builds them, kernel/KaminoSolver.cu:128-153
+        float a = t.triA[i], c = t.triC[i];
+        float b = (float)(t.minusTwoOverH2 - (double)__fdiv_rn(nSq, t.sinSq[i]));
+        if (i == 0) { b = __fadd_rn(b, a); a = 0.0f; }
+        if (i == nT - 1) { b = __fadd_rn(b, c); c = 0.0f; }
+        const double l = (i == 0) ? 0.0 : (double)a / bPrev;
+        const double bp = (double)b - l * cPrev;
+        const float l32 = (float)l;
+        const double invb = 1.0 / bp;
+        if (i % L == 0) beta = 1.0;
+        beta *= -(double)l32;
+        const size_t e = base + (size_t)i * W;
+        t.thL[e] = l32;
+        t.thInvB[e] = (float)invb;
+        t.thBetaInv[e] = (float)(beta * invb);
+        t.thH[e] = (float)((double)c * invb);
+        if (i % L == L - 1) t.thBetaEnd[((size_t)(slot / W) * P + i / L) * W + (slot % W)] = (float)beta;
+        bPrev = bp; cPrev = (double)c;
+    }
+    // backward: delta_i = prod_{m = i .. chunk end} (-h_m) (from the ROUNDED h)
+    double delta = 1.0;
+    for (int i = nT - 1; i >= 0; --i) {
+        if (i % L == L - 1) delta = 1.0;
+        const size_t e = base + (size_t)i * W;
+        delta *= -(double)t.thH[e];
+        t.thDelta[e] = (float)delta;
+    }
+}
+
+// ---- per step -------------------------------------------------------------------------------------
+// grid ((N/2) / W, batch), P * W threads, dynamic smem (P (L W + W) + 2 (P + 1) W) float2 + 2 P W floats.
+// Shared-memory rows of the right-hand sides are padded by one W-run per chunk (pitch L*W + W):
+// the 64-bit accesses of a half-warp (16 / W chunks x W systems) then fall in distinct banks.
+// W, L and P are compile-time so that every loop is fully unrolled: all global loads of a phase
+// are in flight together and the only dependent chains are the FMA recurrences themselves.
+template <int W, int L, int P>
+__global__ void __launch_bounds__(P * W)
+tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    constexpr int nT = P * L;
+    constexpr int kChunkPitch = L * W + W;              // float2 elements per chunk in smem
+    constexpr int kThreads = P * W;
+    const int half = g.nPhi >> 1;
+    float2* d = sm;                                     // P chunks of kChunkPitch
+    float2* carryY = sm + P * kChunkPitch;              // (P + 1) x W : y at the end of chunk p-1
+    float2* carryX = carryY + (P + 1) * W;              // (P + 1) x W : x at the start of chunk p
+    float* betaEnd = reinterpret_cast<float*>(carryX + (P + 1) * W);   // P x W
+    float* deltaStart = betaEnd + P * W;                               // P x W
+    const int tid = threadIdx.x;
+    const int p = tid / W, w = tid % W;
+    float2* spectrum = spectrumAll + (size_t)blockIdx.y * (g.cells >> 1) + (size_t)blockIdx.x * W;
+    const size_t tabBase = (size_t)blockIdx.x * nT * W;
+    const float* tabL = t.thL + tabBase;
+    const float* tabInvB = t.thInvB + tabBase;
+    const float* tabBetaInv = t.thBetaInv + tabBase;
+    const float* tabH = t.thH + tabBase;
+    const float* tabDelta = t.thDelta + tabBase;
+
+    // tables needed first (independent of the previous kernel): my chunk's forward multipliers
+    // and the carry multipliers of the whole block
+    // (multipliers are register-prefetched ahead of the barriers for chunks of up to 16 rows;
+    // longer chunks read them inside the recurrences, 8 rows ahead, to stay within the register file)
+    constexpr bool kPrefetch = (L <= 16);
+    constexpr int kPre = kPrefetch ? L : 1;
+    constexpr int kBatch = L < 16 ? L : 16;             // items per thread per load / store batch
+    const int row0 = p * L;
+    float lReg[kPre];
+    if (kPrefetch) {
+#pragma unroll
+        for (int ii = 0; ii < L; ++ii) lReg[ii] = __ldg(tabL + (row0 + ii) * W + w);
+    }
+    betaEnd[tid] = __ldg(t.thBetaEnd + (size_t)blockIdx.x * P * W + tid);
+    deltaStart[tid] = __ldg(tabDelta + row0 * W + w);
+
+    pdlWait();                                   // the right-hand sides come from the previous kernel
+    // load: item = (row i, system w), runs of W float2 per row; L items per thread
+#pragma unroll 1
+    for (int k0 = 0; k0 < L; k0 += kBatch) {
+        float2 v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int item = tid + (k0 + k) * kThreads;
+            v[k] = spectrum[(size_t)(item / W) * half + (item % W)];
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int item = tid + (k0 + k) * kThreads;
+            const int i = item / W, ww = item % W;
+            d[(i / L) * kChunkPitch + (i % L) * W + ww] = v[k];
+        }
+    }
+    __syncthreads();
+
+    float2* mine = d + p * kChunkPitch + w;
+    // forward recurrence inside the chunk from a zero carry: alpha_i = d_i - l_i alpha_{i-1}
+    {
+        float2 prev = make_float2(0.0f, 0.0f);
+#pragma unroll(kPrefetch ? L : 8)
+        for (int ii = 0; ii < L; ++ii) {
+            const float l = kPrefetch ? lReg[ii] : __ldg(tabL + (row0 + ii) * W + w);
+            float2 v = mine[ii * W];
+            v.x = __fmaf_rn(-l, prev.x, v.x);
+            v.y = __fmaf_rn(-l, prev.y, v.y);
+            mine[ii * W] = v;
+            prev = v;
+        }
+    }
+    // my chunk's backward multipliers: issued now, consumed after the carry chain
+    float invB[kPre], betaInv[kPre], hReg[kPre];
+    if (kPrefetch) {
+#pragma unroll
+        for (int ii = 0; ii < L; ++ii) {
+            const int e = (row0 + ii) * W + w;
+            invB[ii] = __ldg(tabInvB + e);
+            betaInv[ii] = __ldg(tabBetaInv + e);
+            hReg[ii] = __ldg(tabH + e);
+        }
+    }
+    __syncthreads();
+    // chain the chunk carries: Y_p = alpha_end(p) + beta_end(p) Y_{p-1}; carryY[p] = Y_{p-1}
+    if (tid < W) {
+        float2 y = make_float2(0.0f, 0.0f);
+        carryY[tid] = y;
+#pragma unroll 8
+        for (int q = 0; q < P; ++q) {
+            const float2 a = d[q * kChunkPitch + (L - 1) * W + tid];
+            const float be = betaEnd[q * W + tid];
+            y.x = __fmaf_rn(be, y.x, a.x);
+            y.y = __fmaf_rn(be, y.y, a.y);
+            carryY[(q + 1) * W + tid] = y;
+        }
+    }
+    __syncthreads();
+    // backward recurrence inside the chunk from a zero carry:
+    //   t_i = (alpha_i + beta_i Y_{p-1}) / b'_i ;  gamma_i = t_i - h_i gamma_{i+1}
+    {
+        const float2 yPrev = carryY[p * W + w];
+        float2 next = make_float2(0.0f, 0.0f);
+#pragma unroll(kPrefetch ? L : 8)
+        for (int ii = L - 1; ii >= 0; --ii) {
+            const int e = (row0 + ii) * W + w;
+            const float ib = kPrefetch ? invB[ii] : __ldg(tabInvB + e);
+            const float bi = kPrefetch ? betaInv[ii] : __ldg(tabBetaInv + e);
+            const float hh = kPrefetch ? hReg[ii] : __ldg(tabH + e);
+            float2 v = mine[ii * W];
+            v.x = __fmaf_rn(bi, yPrev.x, __fmul_rn(v.x, ib));
+            v.y = __fmaf_rn(bi, yPrev.y, __fmul_rn(v.y, ib));
+            v.x = __fmaf_rn(-hh, next.x, v.x);
+            v.y = __fmaf_rn(-hh, next.y, v.y);
+            mine[ii * W] = v;
+            next = v;
+        }
+    }
+    // delta of my output items (load mapping): issued now, consumed after the carry chain
+    float de[kPre];
+    if (kPrefetch) {
+#pragma unroll
+        for (int k = 0; k < L; ++k) de[k] = __ldg(tabDelta + tid + k * kThreads);
+    }
+    __syncthreads();
+    // chain the carries upwards: X_p = gamma_start(p) + delta_start(p) X_{p+1}; carryX[p] = X_p
+    if (tid < W) {
+        float2 x = make_float2(0.0f, 0.0f);
+        carryX[P * W + tid] = x;
+#pragma unroll 8
+        for (int q = P - 1; q >= 0; --q) {
+            const float2 gm = d[q * kChunkPitch + tid];
+            const float ds = deltaStart[q * W + tid];
+            x.x = __fmaf_rn(ds, x.x, gm.x);
+            x.y = __fmaf_rn(ds, x.y, gm.y);
+            carryX[q * W + tid] = x;
+        }
+    }
+    __syncthreads();
+    // x_i = gamma_i + delta_i X_{p+1}, written back in the load mapping (coalesced)
+#pragma unroll(kPrefetch ? L : 8)
+    for (int k = 0; k < L; ++k) {
+        const int item = tid + k * kThreads;
+        const int i = item / W, ww = item % W;
+        const int q = i / L;
+        const float dl = kPrefetch ? de[k] : __ldg(tabDelta + item);
+        const float2 gm = d[q * kChunkPitch + (i % L) * W + ww];
+        const float2 xn = carryX[(q + 1) * W + ww];
+        spectrum[(size_t)i * half + ww] = make_float2(__fmaf_rn(dl, xn.x, gm.x), __fmaf_rn(dl, xn.y, gm.y));
+    }
+}
+
+template <int W, int L, int P>
+cudaError_t launchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, const TriLaunch& l,
                       cudaStream_t stream, bool configureOnly)
 {
     if (configureOnly)
-        return cudaFuncSetAttribute(tridiagonalKernel<W, THREADS, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return cudaFuncSetAttribute(tridiagonalKernel<W, L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
     dim3 grid((g.nPhi / 2) / W, batch);
-    return launchChained(tridiagonalKernel<W, THREADS, STAGE>, grid, dim3(THREADS), smem, stream, g, t, spectrum);
+    return launchChained(tridiagonalKernel<W, L, P>, grid, dim3(P * W), l.smem, stream, g, t, spectrum);
 }
 
 cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
                         cudaStream_t stream, bool configureOnly)
 {
-    const TriLaunch l = triLaunch(g);
-#define KB_TRI(WW, TT, SS) if (l.W == WW && l.threads == TT && l.stage == SS) return launchTri<WW, TT, SS>(g, t, spectrum, batch, l.smem, stream, configureOnly)
-    KB_TRI(2, 64, true); KB_TRI(2, 256, true); KB_TRI(2, 512, true);
-    KB_TRI(4, 64, true); KB_TRI(4, 256, true); KB_TRI(4, 512, true);
-    KB_TRI(2, 512, false); KB_TRI(4, 512, false); KB_TRI(8, 512, false);
+    const TriLaunch l = triLaunch(g, batch);
+#define KB_TRI(WW, LL, PP) if (l.W == WW && l.L == LL && l.P == PP) return launchTri<WW, LL, PP>(g, t, spectrum, batch, l, stream, configureOnly)
+#define KB_TRI_W(LL, PP) KB_TRI(2, LL, PP); KB_TRI(4, LL, PP); KB_TRI(8, LL, PP)
+    KB_TRI_W(4, 4); KB_TRI_W(4, 8); KB_TRI_W(4, 16);          // nTheta = 16, 32, 64
+    KB_TRI_W(8, 16); KB_TRI_W(8, 32);                         // 128, 256
+    KB_TRI_W(16, 32); KB_TRI_W(16, 64);                       // 512, 1024
+    KB_TRI_W(32, 64);                                         // 2048
+    KB_TRI(2, 32, 128); KB_TRI(4, 32, 128); KB_TRI(8, 32, 128);   // 4096
+    KB_TRI(2, 64, 128); KB_TRI(4, 64, 128);                   // 8192
+#undef KB_TRI_W
 #undef KB_TRI
     return cudaErrorInvalidValue;
 }
 
 } // namespace
 
-size_t crTableFloats(const GridParams& g)
+size_t solveTableFloats(const GridParams& g)
 {
-    // fwd: nTheta x N/2 float2, bwd a/b/c: 3 x nTheta x N/2 floats
-    return (size_t)g.nTheta * (g.nPhi / 2) * 5;
+    // l, 1/b', beta/b', h, delta: 5 x nTheta x N/2 floats, + beta at the chunk ends (<= nTheta/4 x N/2)
+    return (size_t)g.nTheta * (g.nPhi / 2) * 5 + (size_t)(g.nTheta / 4) * (g.nPhi / 2);
 }
 
-cudaError_t configureTridiagonal(const GridParams& g)
+cudaError_t configureTridiagonal(const GridParams& g, int batch)
 {
     SpectralTables none{};
-    return dispatchTri(g, none, nullptr, 1, nullptr, true);
+    return dispatchTri(g, none, nullptr, batch, nullptr, true);
 }
 
-cudaError_t launchBuildCrTables(const GridParams& g, SpectralTables t, cudaStream_t stream)
+cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream)
 {
-    const size_t smem = 3 * sizeof(float) * (size_t)g.nTheta;
-    cudaError_t e = cudaFuncSetAttribute(buildCrTablesKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int threads = g.nTheta / 2 < 256 ? (g.nTheta / 2 < 32 ? 32 : g.nTheta / 2) : 256;
-    buildCrTablesKernel<<<g.nPhi / 2, threads, smem, stream>>>(g, t, triLaunch(g).W);
+    const TriLaunch l = triLaunch(g, batch);
+    const int half = g.nPhi / 2;
+    const int threads = 64;
+    buildSolveTablesKernel<<<(half + threads - 1) / threads, threads, 0, stream>>>(g, t, l.W, l.L);
     return cudaGetLastError();
 }
 
