@@ -123,6 +123,29 @@ int kamino_geometric(kamino_ctx* ctx);
  * KAMINO_PRESSURE. */
 int kamino_project(kamino_ctx* ctx);
 
+/* ---- theta-band entry points -----------------------------------------------------------
+ * The reference is single-GPU (device 0 hard-coded, kernel/KaminoSolver.cu:20); these have no
+ * counterpart there. A band-decomposed run (kaminogpu_b200/banded.py: one process per GPU,
+ * NCCL halo exchange + all-to-all around the theta solve) keeps full-size buffers on every
+ * rank and asks each kernel of the step for a range of GLOBAL theta rows only. Same kernels,
+ * same arithmetic as kamino_advect / kamino_geometric / kamino_project, so a banded run is
+ * bit-identical to the single-GPU run. Asynchronous on the context's stream; single-
+ * simulation contexts without particles. Row ranges: multiples of 8 rows for advect and
+ * geometric, of 2 for divergence_fft; buffers swap exactly as in the phase calls. */
+int kamino_band_advect(kamino_ctx* ctx, int rowBegin, int rowCount);
+int kamino_band_geometric(kamino_ctx* ctx, int rowBegin, int rowCount);
+/* divergence + forward FFT of rows [rowBegin, rowBegin+rowCount) into the spectrum buffer
+ * ([theta][slot], nPhi/2 float2 per row; slot k = wavenumber k, slot 0 = Nyquist). */
+int kamino_band_divergence_fft(kamino_ctx* ctx, int rowBegin, int rowCount);
+/* theta solve of slots [slotBegin, slotBegin+slotCount) (multiples of 8) for ALL rows, in place
+ * on a packed device buffer [nTheta][pitch] of float2 (what the all-to-all delivers). */
+int kamino_band_tridiagonal(kamino_ctx* ctx, void* packedSpectrum, int pitch, int slotBegin, int slotCount);
+/* inverse FFT + gradient subtraction of rows [rowBegin, rowBegin+rowCount); reads spectrum rows
+ * rowBegin .. rowBegin+rowCount (one past the band, unless it is the last row of the grid). */
+int kamino_band_inverse_fft_gradient(kamino_ctx* ctx, int rowBegin, int rowCount);
+/* device pointer of the half-spectrum buffer of simulation `sim` (nTheta x nPhi/2 float2). */
+int kamino_spectrum_device_ptr(kamino_ctx* ctx, int sim, void** devicePtr);
+
 /* KaminoSolver::stepForward (kernel/KaminoSolver.cu:197-221) nSteps times, launched as
  * CUDA graphs on the context's stream. Asynchronous: returns once the work is queued. */
 int kamino_step(kamino_ctx* ctx, int nSteps);

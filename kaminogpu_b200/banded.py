@@ -1,0 +1,303 @@
+"""Theta-band decomposition of ONE simulation over P GPUs (BASELINE config 5).
+
+The reference is single-GPU (device 0 hard-coded, kernel/KaminoSolver.cu:20) and cannot even
+launch its theta solve above nTheta = 2048 (kernel/KaminoCore.cu:779-782), so this mode has no
+reference counterpart; its contract is bit-identity with this package's own single-GPU step,
+which the tests check.
+
+One process per GPU (torch.distributed, NCCL over NVLink). Rank r owns the theta rows
+[r nT/P, (r+1) nT/P) of u_phi, u_theta, density and pressure. Every rank keeps FULL-SIZE
+buffers (global row indices everywhere, 46 B/cell: 6.2 GB at 8192 x 16384) and asks each kernel of
+the step for its rows only (kamino_band_* entry points of the C ABI). Per step:
+
+  1. halo exchange   HALO = 24 rows of u_phi, u_theta, density from each neighbour (P2P send/recv)
+  2. advection       on [lo-16, hi+16): the 16 extra rows are recomputed locally instead of being
+                     exchanged a second time (backtraces reach < 4 rows: theta-CFL < 1, RK midpoint,
+                     bilinear stencil)
+  3. geometric       on [lo-8, hi+8)   (its staggered re-averaging reaches one row)
+  4. divergence+FFT  on [lo, hi)       -> spectrum rows [lo, hi), all wavenumbers
+  5. all-to-all      [band rows][all k] -> [all rows][k band]           (NCCL all_to_all_single)
+  6. theta solve     for the rank's wavenumber band, in place on the packed receive buffer
+  7. all-to-all back, plus one spectrum row from the next rank (the theta gradient of the last
+     band row needs p of row hi)
+  8. inverse FFT + gradient on [lo, hi)
+
+Tracer particles are not band-decomposed (they would migrate between ranks); banded contexts
+carry none.
+
+`LocalGroup` runs the same per-rank phases for P virtual ranks inside one process, on one GPU,
+replacing the NCCL calls by device copies: that is what the single-GPU parity test drives.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .solver import KaminoSolver
+
+HALO = 24          # rows exchanged with each neighbour
+ADVECT_EXTRA = 16  # rows beyond the band that the advection recomputes
+GEO_EXTRA = 8      # rows beyond the band that the geometric phase recomputes
+
+
+class BandPlan:
+    """Row / wavenumber ranges of every rank."""
+
+    def __init__(self, nTheta, world):
+        if nTheta % world:
+            raise ValueError("nTheta must be divisible by the number of bands")
+        self.nTheta, self.world = nTheta, world
+        self.rows = nTheta // world
+        self.half = nTheta                    # nPhi / 2 wavenumber slots
+        self.kper = self.half // world
+        if world > 1 and (self.rows < 32 or self.rows % 8 or self.kper % 8):
+            raise ValueError("bands need >= 32 rows, a multiple of 8 rows and of 8 wavenumbers per rank")
+
+    def band(self, r):
+        return r * self.rows, (r + 1) * self.rows
+
+    def clipped(self, r, extra):
+        lo, hi = self.band(r)
+        return max(lo - extra, 0), min(hi + extra, self.nTheta)
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class BandLayout:
+    """Which rows / spectrum blocks a rank sends and receives: pure tensor slicing, shared by the
+    GPU rank (BandRank) and the CPU stand-in of the gloo tests. Needs: plan, rank, world, lo, hi,
+    fields() -> [u_phi, u_theta, density] full-size [nTheta][nPhi] tensors, spectrum
+    [nTheta][nPhi/2][2], send / recv [world][rows][kper][2]."""
+
+    # ---- halos: (tensor, row range) pairs ------------------------------------------------------
+    def halo_sends(self):
+        """[(to_rank, tensor)] : my top HALO rows go up, my bottom HALO rows go down."""
+        ops = []
+        for f in self.fields():
+            if self.rank > 0:
+                ops.append((self.rank - 1, f[self.lo:self.lo + HALO]))
+            if self.rank < self.world - 1:
+                ops.append((self.rank + 1, f[self.hi - HALO:self.hi]))
+        return ops
+
+    def halo_recvs(self):
+        ops = []
+        for f in self.fields():
+            if self.rank > 0:
+                ops.append((self.rank - 1, f[self.lo - HALO:self.lo]))
+            if self.rank < self.world - 1:
+                ops.append((self.rank + 1, f[self.hi:self.hi + HALO]))
+        return ops
+
+    def pack_forward(self):
+        """[band rows][all k] -> send[dest][band rows][k of dest]."""
+        rows, kper, P = self.plan.rows, self.plan.kper, self.world
+        self.send.copy_(self.spectrum[self.lo:self.hi].view(rows, P, kper, 2).permute(1, 0, 2, 3))
+        return self.send
+
+    def unpack_backward(self, packed):
+        """packed[src][band rows][k of src] -> spectrum[band rows][all k]."""
+        rows, kper, P = self.plan.rows, self.plan.kper, self.world
+        self.spectrum[self.lo:self.hi].view(rows, P, kper, 2).copy_(packed.permute(1, 0, 2, 3))
+
+    def spectrum_row(self, j):
+        return self.spectrum[j]
+
+
+class BandRank(BandLayout):
+    """The state and compute phases of one rank (no communication in here)."""
+
+    def __init__(self, nTheta, radius, dt, rank, world, device=0):
+        import torch
+        self.torch = torch
+        self.plan = BandPlan(nTheta, world)
+        self.rank, self.world, self.device = rank, world, device
+        self.nTheta, self.nPhi = nTheta, 2 * nTheta
+        self.solver = KaminoSolver(self.nPhi, nTheta, radius, dt, device=device)
+        self.lib, self.ctx = self.solver._lib, self.solver._ctx
+        self.lo, self.hi = self.plan.band(rank)
+        half = self.plan.half
+        p = ctypes.c_void_p()
+        capi.check(self.lib.kamino_spectrum_device_ptr(self.ctx, 0, ctypes.byref(p)), self.ctx)
+        self.spectrum = self._wrap(p.value, (nTheta, half, 2))
+        rows, kper = self.plan.rows, self.plan.kper
+        dev = torch.device("cuda", device)
+        self.send = torch.empty((world, rows, kper, 2), dtype=torch.float32, device=dev)
+        self.recv = torch.empty((world, rows, kper, 2), dtype=torch.float32, device=dev)
+
+    def close(self):
+        self.solver.close()
+
+    def _wrap(self, ptr, shape):
+        return self.torch.as_tensor(_CudaArray(ptr, shape), device=self.torch.device("cuda", self.device))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.solver.set_stream(cuda_stream_ptr)
+
+    def fields(self):
+        """Full-size torch views of the this-step u_phi, u_theta, density (pointers move with the swaps)."""
+        out = []
+        for field in (capi.VEL_PHI, capi.VEL_THETA, capi.DENSITY):
+            p, pitch = ctypes.c_void_p(), ctypes.c_size_t()
+            capi.check(self.lib.kamino_field_device_ptr(self.ctx, field, 0, 0, ctypes.byref(p), ctypes.byref(pitch)),
+                       self.ctx)
+            out.append(self._wrap(p.value, (self.nTheta, self.nPhi)))
+        return out
+
+    # ---- compute phases ----------------------------------------------------------------------------
+    def advect_to_spectrum(self):
+        a0, a1 = self.plan.clipped(self.rank, ADVECT_EXTRA)
+        g0, g1 = self.plan.clipped(self.rank, GEO_EXTRA)
+        capi.check(self.lib.kamino_band_advect(self.ctx, a0, a1 - a0), self.ctx)
+        capi.check(self.lib.kamino_band_geometric(self.ctx, g0, g1 - g0), self.ctx)
+        capi.check(self.lib.kamino_band_divergence_fft(self.ctx, self.lo, self.hi - self.lo), self.ctx)
+
+    def solve(self, packed):
+        """packed = [all rows][my k band] (the receive buffer of the forward all-to-all), in place."""
+        kper = self.plan.kper
+        capi.check(self.lib.kamino_band_tridiagonal(self.ctx, ctypes.c_void_p(packed.data_ptr()), kper,
+                                                    self.rank * kper, kper), self.ctx)
+
+    def inverse(self):
+        capi.check(self.lib.kamino_band_inverse_fft_gradient(self.ctx, self.lo, self.hi - self.lo), self.ctx)
+
+    # ---- host access (tests, start-up) ----------------------------------------------------------------
+    def download_band(self):
+        """numpy copies of my rows of u_phi, u_theta (clipped to nTheta-1 rows), density."""
+        self.solver.sync()
+        u, v, rho = [f.cpu().numpy() for f in self.fields()]
+        return u[self.lo:self.hi].copy(), v[self.lo:min(self.hi, self.nTheta - 1)].copy(), rho[self.lo:self.hi].copy()
+
+
+# ---- communication: free functions over torch tensors, so that they also run on CPU with gloo ----------
+
+def exchange(sends, recvs, dist):
+    """Post all receives and sends of one neighbour exchange ((peer, tensor) pairs) and wait."""
+    ops = [dist.P2POp(dist.irecv, t, peer) for peer, t in recvs] + [dist.P2POp(dist.isend, t, peer) for peer, t in sends]
+    if not ops:
+        return
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def all_to_all(recv, send, dist):
+    """recv[src] <- send[dest] of rank src; both [world][...] contiguous with equal blocks."""
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(recv.view(-1), send.view(-1))
+        return
+    # gloo (CPU tests): pairwise exchange
+    rank, world = dist.get_rank(), dist.get_world_size()
+    recv[rank].copy_(send[rank])
+    ops = []
+    for peer in range(world):
+        if peer != rank:
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+            ops.append(dist.P2POp(dist.isend, send[peer], peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class DistributedBandedSolver:
+    """One rank of a band-decomposed simulation under torch.distributed."""
+
+    def __init__(self, nTheta, radius, dt, device=0):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.r = BandRank(nTheta, radius, dt, self.rank, self.world, device)
+        # kernels, torch copies and the NCCL calls are ordered on torch's current stream
+        self.r.set_stream(self.r.torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        self.r.close()
+
+    def step(self, nSteps=1):
+        r, dist = self.r, self.dist
+        for _ in range(nSteps):
+            if self.world > 1:
+                exchange(r.halo_sends(), r.halo_recvs(), dist)
+            r.advect_to_spectrum()
+            if self.world > 1:
+                all_to_all(r.recv, r.pack_forward(), dist)
+                packed = r.recv
+            else:
+                packed = r.pack_forward()
+            r.solve(packed.view(r.nTheta, r.plan.kper, 2))
+            if self.world > 1:
+                all_to_all(r.send, packed, dist)
+                r.unpack_backward(r.send)
+                # the theta gradient of my last row needs the pressure spectrum of row hi
+                sends = [(self.rank - 1, r.spectrum_row(r.lo))] if self.rank > 0 else []
+                recvs = [(self.rank + 1, r.spectrum_row(r.hi))] if self.rank < self.world - 1 else []
+                exchange(sends, recvs, dist)
+            else:
+                r.unpack_backward(packed)
+            r.inverse()
+
+
+class LocalGroup:
+    """P virtual ranks in one process on one GPU: the same phases, device copies instead of NCCL."""
+
+    def __init__(self, nTheta, radius, dt, world, device=0):
+        self.ranks = [BandRank(nTheta, radius, dt, r, world, device) for r in range(world)]
+        self.world = world
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
+
+    def sync(self):
+        for r in self.ranks:
+            r.solver.sync()
+        self.ranks[0].torch.cuda.synchronize()
+
+    def step(self, nSteps=1):
+        R = self.ranks
+        for _ in range(nSteps):
+            self.sync()
+            sends = {r.rank: r.halo_sends() for r in R}
+            for r in R:
+                # my k-th receive from `peer` pairs with peer's k-th send to me (same field order)
+                mine = r.halo_recvs()
+                for peer in {p for p, _ in mine}:
+                    src = [t for to, t in sends[peer] if to == r.rank]
+                    dst = [t for frm, t in mine if frm == peer]
+                    for s, d in zip(src, dst):
+                        d.copy_(s)
+            self.sync()
+            for r in R:
+                r.advect_to_spectrum()
+            self.sync()
+            packs = [r.pack_forward() for r in R]
+            self.sync()
+            for r in R:
+                for q in R:
+                    r.recv[q.rank].copy_(packs[q.rank][r.rank])
+            self.sync()
+            for r in R:
+                r.solve(r.recv.view(r.nTheta, r.plan.kper, 2))
+            self.sync()
+            for r in R:
+                for q in R:
+                    r.send[q.rank].copy_(q.recv[r.rank])
+            self.sync()
+            for r in R:
+                r.unpack_backward(r.send)
+            self.sync()
+            for r in R:
+                if r.rank < self.world - 1:
+                    r.spectrum_row(r.hi).copy_(R[r.rank + 1].spectrum_row(r.hi))
+            self.sync()
+            for r in R:
+                r.inverse()
+        self.sync()
+
+    def gather(self):
+        """The global u_phi, u_theta, density assembled from the bands (numpy)."""
+        parts = [r.download_band() for r in self.ranks]
+        return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(3))

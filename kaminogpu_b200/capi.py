@@ -43,6 +43,12 @@ SIGNATURES = {
     "kamino_advect": (ctypes.c_int, [ctypes.c_void_p]),
     "kamino_geometric": (ctypes.c_int, [ctypes.c_void_p]),
     "kamino_project": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_band_advect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kamino_band_geometric": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kamino_band_divergence_fft": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kamino_band_tridiagonal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "kamino_band_inverse_fft_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kamino_spectrum_device_ptr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "kamino_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kamino_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "kamino_run_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

@@ -118,7 +118,7 @@ advectKernel(GridParams g, AdvectArgs a)
         const float* density = pinPointer(a.density + (size_t)sim * g.cells);
         const int log2TilesX = g.log2NPhi - 5;
         const int i0 = (block & ((1 << log2TilesX) - 1)) << 5;
-        const int j0 = (block >> log2TilesX) * kTileRows;
+        const int j0 = g.rowBegin + (block >> log2TilesX) * kTileRows;
         SamplerRegs tr = sr;
         tr.tileRow0 = j0 - 2;
         tr.tileCol0 = i0 - 4;
@@ -198,7 +198,7 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
 {
     // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget), default 5
     static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 5; }();
-    a.tileBlocks = (g.nPhi / 32) * (g.nTheta / kTileRows);
+    a.tileBlocks = (g.nPhi / 32) * (g.rowCount / kTileRows);      // rowBegin, rowCount: multiples of kTileRows
     const int blocksParticles = (a.particles && g.numParticles > 0)
         ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
     dim3 grid(a.tileBlocks + blocksParticles, batch);

@@ -31,6 +31,10 @@ struct GridParams {
     float cofTheta;    // dt / radius                (kernel/KaminoCore.cu:204)
     size_t cells;      // nTheta * nPhi : per-simulation stride of every field buffer
     long numParticles; // per simulation
+    // theta band this launch works on (rows rowBegin .. rowBegin + rowCount - 1 of the GLOBAL grid;
+    // the whole grid unless a kamino_band_* entry point narrowed it). Arrays and indices stay
+    // global: a band-decomposed run keeps full-size buffers and only computes its rows.
+    int rowBegin, rowCount;
 };
 
 // Field buffers of the whole batch; simulation b starts at ptr + b * cells.

@@ -105,7 +105,7 @@ float* fieldBuffer(kamino_ctx* ctx, int field, int which)
 // enqueue the kernels of one phase on `s`, using and updating the index state `st`
 struct IndexState { int vel, density, particle; };
 
-cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
+AdvectArgs advectArgs(kamino_ctx* ctx, const IndexState& st)
 {
     AdvectArgs a{};
     a.velPhi = ctx->velPhi[st.vel];
@@ -119,7 +119,12 @@ cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
     a.cofPhiCentred = ctx->tables.cofPhiCentred;
     a.cofPhiTheta = ctx->tables.cofPhiTheta;
     a.consts = ctx->tables.samplerConsts;
-    cudaError_t e = launchAdvect(ctx->g, a, ctx->batch, s);
+    return a;
+}
+
+cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
+{
+    cudaError_t e = launchAdvect(ctx->g, advectArgs(ctx, st), ctx->batch, s);
     st.vel ^= 1; st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
     return e;
 }
@@ -299,6 +304,8 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
     g.cofTheta = dt / radius;
     g.cells = (size_t)g.nTheta * g.nPhi;
     g.numParticles = particlesPerSim;
+    g.rowBegin = 0;
+    g.rowCount = nTheta;
 
     const size_t fieldBytes = alignUp(sizeof(float) * g.cells * batch, 256);
     const size_t tableBytes = alignUp(spectralTableBytes(g), 256);
@@ -489,6 +496,87 @@ int kamino_project(kamino_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
     return timedPhase(ctx, ctx->projectionTime, [&](IndexState& st) { return enqueueProject(ctx, st, ctx->stream); });
+}
+
+// ---- theta-band entry points (band-decomposed multi-GPU runs, kaminogpu_b200/banded.py) ----------
+
+static int bandRange(kamino_ctx* ctx, int rowBegin, int rowCount, int multiple, GridParams* out)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (ctx->batch != 1) return fail(ctx, KAMINO_ERR_STATE, "band entry points need a single-simulation context");
+    if (rowBegin < 0 || rowCount <= 0 || rowBegin + rowCount > ctx->g.nTheta || rowBegin % multiple || rowCount % multiple)
+        return fail(ctx, KAMINO_ERR_INVALID, "band rows out of range or not a multiple of the kernel's row granularity");
+    *out = ctx->g;
+    out->rowBegin = rowBegin;
+    out->rowCount = rowCount;
+    out->numParticles = 0;          // particles are not band-decomposed
+    return 0;
+}
+
+int kamino_band_advect(kamino_ctx* ctx, int rowBegin, int rowCount)
+{
+    GridParams g;
+    if (int rc = bandRange(ctx, rowBegin, rowCount, 8, &g)) return rc;
+    DeviceGuard guard(ctx->device);
+    IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
+    AdvectArgs a = advectArgs(ctx, st);
+    a.particles = nullptr; a.particlesOut = nullptr;
+    KB_TRY(ctx, launchAdvect(g, a, 1, ctx->stream));
+    ctx->velIdx ^= 1; ctx->densityIdx ^= 1;
+    return 0;
+}
+
+int kamino_band_geometric(kamino_ctx* ctx, int rowBegin, int rowCount)
+{
+    GridParams g;
+    if (int rc = bandRange(ctx, rowBegin, rowCount, 8, &g)) return rc;
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, launchGeometric(g, ctx->tables, ctx->velPhi[ctx->velIdx], ctx->velTheta[ctx->velIdx],
+                                ctx->velPhi[ctx->velIdx ^ 1], ctx->velTheta[ctx->velIdx ^ 1], 1, ctx->stream));
+    ctx->velIdx ^= 1;
+    return 0;
+}
+
+int kamino_band_divergence_fft(kamino_ctx* ctx, int rowBegin, int rowCount)
+{
+    GridParams g;
+    if (int rc = bandRange(ctx, rowBegin, rowCount, 2, &g)) return rc;
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, launchDivergenceFFT(g, ctx->tables, ctx->velPhi[ctx->velIdx], ctx->velTheta[ctx->velIdx],
+                                    ctx->spectrum, 1, ctx->stream));
+    return 0;
+}
+
+int kamino_band_tridiagonal(kamino_ctx* ctx, void* packedSpectrum, int pitch, int slotBegin, int slotCount)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (ctx->batch != 1) return fail(ctx, KAMINO_ERR_STATE, "band entry points need a single-simulation context");
+    const int half = ctx->g.nPhi / 2;
+    if (!packedSpectrum || pitch < slotCount || slotBegin < 0 || slotCount <= 0 || slotBegin + slotCount > half)
+        return fail(ctx, KAMINO_ERR_INVALID, "bad packed spectrum, pitch or slot range");
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = launchTridiagonalBand(ctx->g, ctx->tables, (float2*)packedSpectrum, pitch, slotBegin, slotCount,
+                                          ctx->batch, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "kamino_band_tridiagonal (slot range must be a multiple of 8)");
+    return 0;
+}
+
+int kamino_band_inverse_fft_gradient(kamino_ctx* ctx, int rowBegin, int rowCount)
+{
+    GridParams g;
+    if (int rc = bandRange(ctx, rowBegin, rowCount, 1, &g)) return rc;
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, launchInverseFFTGradient(g, ctx->tables, ctx->spectrum, ctx->velPhi[ctx->velIdx],
+                                         ctx->velTheta[ctx->velIdx], ctx->pressure, 1, ctx->stream));
+    return 0;
+}
+
+int kamino_spectrum_device_ptr(kamino_ctx* ctx, int sim, void** devicePtr)
+{
+    if (int rc = checkSim(ctx, sim)) return rc;
+    if (!devicePtr) return fail(ctx, KAMINO_ERR_INVALID, "NULL output");
+    *devicePtr = ctx->spectrum + (size_t)sim * (ctx->g.cells >> 1);
+    return 0;
 }
 
 int kamino_step(kamino_ctx* ctx, int nSteps)

@@ -75,6 +75,10 @@ cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, co
                                 const float* velTheta, float2* spectrum, int batch, cudaStream_t stream);
 cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
                               cudaStream_t stream);
+// band-decomposed runs: solve slots [slotBegin, slotBegin + slotCount) whose right-hand sides sit in
+// `packed` as [theta][slot - slotBegin] with row pitch `pitch` (float2 elements), one simulation
+cudaError_t launchTridiagonalBand(const GridParams& g, const SpectralTables& t, float2* packed, int pitch,
+                                  int slotBegin, int slotCount, int tableBatch, cudaStream_t stream);
 // velPhi / velTheta updated in place; pressure (may be NULL) receives p.
 cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
                                      float* velPhi, float* velTheta, float* pressure, int batch,

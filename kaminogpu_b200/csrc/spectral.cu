@@ -145,8 +145,8 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
     __shared__ __align__(8) uint64_t twBar;
     const int N = g.nPhi, half = N >> 1, log2T = g.log2NPhi - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
-    const int pairs = g.nTheta >> 1;
-    const int pairRaw = blockIdx.x * (BLOCK >> log2T) + local;
+    const int pairs = (g.rowBegin + g.rowCount) >> 1;             // one past the last pair of the band
+    const int pairRaw = (g.rowBegin >> 1) + blockIdx.x * (BLOCK >> log2T) + local;
     const bool valid = pairRaw < pairs;
     const int j = 2 * (valid ? pairRaw : pairs - 1);
     float2* twShared = smem;
@@ -231,9 +231,10 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
     __shared__ __align__(8) uint64_t twBar;
     const int N = g.nPhi, half = N >> 1, nT = g.nTheta, log2T = g.log2NPhi - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
-    const int rowRaw = blockIdx.x * (BLOCK >> log2T) + local;
-    const bool valid = rowRaw < nT;
-    const int j = valid ? rowRaw : nT - 1;
+    const int rowEnd = g.rowBegin + g.rowCount;
+    const int rowRaw = g.rowBegin + blockIdx.x * (BLOCK >> log2T) + local;
+    const bool valid = rowRaw < rowEnd;
+    const int j = valid ? rowRaw : rowEnd - 1;
     float2* twShared = smem;
     float2* buf = smem + (STAGE ? N : 0) + (size_t)local * fft::paddedSize(N);
     const int sim = blockIdx.y;
@@ -343,11 +344,11 @@ cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t,
         return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
     }
     if (which == 1) {
-        const int pairs = g.nTheta / 2;
+        const int pairs = g.rowCount / 2;
         dim3 grid((pairs + l.perBlock - 1) / l.perBlock, batch);
         return launchChained(divergenceFFTKernel<BLOCK, STAGE>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum);
     } else {
-        dim3 grid((g.nTheta + l.perBlock - 1) / l.perBlock, batch);
+        dim3 grid((g.rowCount + l.perBlock - 1) / l.perBlock, batch);
         return launchChained(inverseFFTGradientKernel<BLOCK, STAGE>, grid, dim3(BLOCK), l.smem, stream, g, t,
                              (const float2*)spectrum, velPhi, velTheta, pressure);
     }

@@ -111,13 +111,14 @@ __global__ void buildSolveTablesKernel(GridParams g, SpectralTables t, int W, in
 // are in flight together and the only dependent chains are the FMA recurrences themselves.
 template <int W, int L, int P>
 __global__ void __launch_bounds__(P * W)
-tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll)
+tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int pitch, int groupOffset)
 {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int nT = P * L;
     constexpr int kChunkPitch = L * W + W;              // float2 elements per chunk in smem
     constexpr int kThreads = P * W;
-    const int half = g.nPhi >> 1;
+    const int half = pitch;                             // row pitch of the spectrum buffer (float2)
+    const int group = blockIdx.x + groupOffset;         // slot group: selects the table slice
     float2* d = sm;                                     // P chunks of kChunkPitch
     float2* carryY = sm + P * kChunkPitch;              // (P + 1) x W : y at the end of chunk p-1
     float2* carryX = carryY + (P + 1) * W;              // (P + 1) x W : x at the start of chunk p
@@ -126,7 +127,7 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
     const int tid = threadIdx.x;
     const int p = tid / W, w = tid % W;
     float2* spectrum = spectrumAll + (size_t)blockIdx.y * (g.cells >> 1) + (size_t)blockIdx.x * W;
-    const size_t tabBase = (size_t)blockIdx.x * nT * W;
+    const size_t tabBase = (size_t)group * nT * W;
     const float* tabL = t.thL + tabBase;
     const float* tabInvB = t.thInvB + tabBase;
     const float* tabBetaInv = t.thBetaInv + tabBase;
@@ -146,7 +147,7 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
 #pragma unroll
         for (int ii = 0; ii < L; ++ii) lReg[ii] = __ldg(tabL + (row0 + ii) * W + w);
     }
-    betaEnd[tid] = __ldg(t.thBetaEnd + (size_t)blockIdx.x * P * W + tid);
+    betaEnd[tid] = __ldg(t.thBetaEnd + (size_t)group * P * W + tid);
     deltaStart[tid] = __ldg(tabDelta + row0 * W + w);
 
     pdlWait();                                   // the right-hand sides come from the previous kernel
@@ -264,19 +265,20 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
 
 template <int W, int L, int P>
 cudaError_t launchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, const TriLaunch& l,
-                      cudaStream_t stream, bool configureOnly)
+                      cudaStream_t stream, bool configureOnly, int pitch, int slotBegin, int slotCount)
 {
     if (configureOnly)
         return cudaFuncSetAttribute(tridiagonalKernel<W, L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
-    dim3 grid((g.nPhi / 2) / W, batch);
-    return launchChained(tridiagonalKernel<W, L, P>, grid, dim3(P * W), l.smem, stream, g, t, spectrum);
+    if (slotBegin % W != 0 || slotCount % W != 0) return cudaErrorInvalidValue;
+    dim3 grid(slotCount / W, batch);
+    return launchChained(tridiagonalKernel<W, L, P>, grid, dim3(P * W), l.smem, stream, g, t, spectrum, pitch, slotBegin / W);
 }
 
 cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
-                        cudaStream_t stream, bool configureOnly)
+                        cudaStream_t stream, bool configureOnly, int tableBatch, int pitch, int slotBegin, int slotCount)
 {
-    const TriLaunch l = triLaunch(g, batch);
-#define KB_TRI(WW, LL, PP) if (l.W == WW && l.L == LL && l.P == PP) return launchTri<WW, LL, PP>(g, t, spectrum, batch, l, stream, configureOnly)
+    const TriLaunch l = triLaunch(g, tableBatch);      // the tables were laid out for this W at creation
+#define KB_TRI(WW, LL, PP) if (l.W == WW && l.L == LL && l.P == PP) return launchTri<WW, LL, PP>(g, t, spectrum, batch, l, stream, configureOnly, pitch, slotBegin, slotCount)
 #define KB_TRI_W(LL, PP) KB_TRI(2, LL, PP); KB_TRI(4, LL, PP); KB_TRI(8, LL, PP)
     KB_TRI_W(4, 4); KB_TRI_W(4, 8); KB_TRI_W(4, 16);          // nTheta = 16, 32, 64
     KB_TRI_W(8, 16); KB_TRI_W(8, 32);                         // 128, 256
@@ -300,7 +302,7 @@ size_t solveTableFloats(const GridParams& g)
 cudaError_t configureTridiagonal(const GridParams& g, int batch)
 {
     SpectralTables none{};
-    return dispatchTri(g, none, nullptr, batch, nullptr, true);
+    return dispatchTri(g, none, nullptr, batch, nullptr, true, batch, g.nPhi / 2, 0, g.nPhi / 2);
 }
 
 cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream)
@@ -315,7 +317,13 @@ cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int ba
 cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
                               cudaStream_t stream)
 {
-    return dispatchTri(g, t, spectrum, batch, stream, false);
+    return dispatchTri(g, t, spectrum, batch, stream, false, batch, g.nPhi / 2, 0, g.nPhi / 2);
+}
+
+cudaError_t launchTridiagonalBand(const GridParams& g, const SpectralTables& t, float2* packed, int pitch,
+                                  int slotBegin, int slotCount, int tableBatch, cudaStream_t stream)
+{
+    return dispatchTri(g, t, packed, 1, stream, false, tableBatch, pitch, slotBegin, slotCount);
 }
 
 } // namespace kb

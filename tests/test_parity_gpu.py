@@ -525,3 +525,33 @@ def test_cli_runs_config_file(K, tmp_path):
             assert raw[:5] == b"BgeoV"
             version, points = struct.unpack(">ii", raw[5:13])
             assert version == 5 and points == npts
+
+
+# ---- theta-band decomposition: virtual ranks on one GPU ----------------------------
+
+@pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
+def test_banded_step_is_bit_identical_to_single_gpu(K, nT, world):
+    """P virtual ranks (kaminogpu_b200.banded.LocalGroup: the per-rank phases of the multi-GPU
+    driver with device copies in place of NCCL) against the ordinary single-context step:
+    u_phi, u_theta and density bit-identical after 3 steps."""
+    from kaminogpu_b200 import banded
+    N = 2 * nT
+    rho0 = oa.synthetic_density(nT).reshape(nT, N)
+    with K.KaminoSolver(N, nT, 5.0, 0.005) as s:
+        s.density.cpuBuffer[:] = rho0
+        s.density.copyToGPU()
+        s.stepForward(0.005, nSteps=3)
+        s.sync()
+        ref = state(s)
+    grp = banded.LocalGroup(nT, 5.0, 0.005, world)
+    try:
+        for r in grp.ranks:
+            r.solver.density.cpuBuffer[:] = rho0
+            r.solver.density.copyToGPU()
+        grp.step(3)
+        u, v, rho = grp.gather()
+    finally:
+        grp.close()
+    assert np.array_equal(u.ravel(), ref["velPhi"])
+    assert np.array_equal(v.ravel(), ref["velTheta"])
+    assert np.array_equal(rho.ravel(), ref["density"])
