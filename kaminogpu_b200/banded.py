@@ -210,13 +210,23 @@ class DistributedBandedSolver:
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.r = BandRank(nTheta, radius, dt, self.rank, self.world, device)
-        # kernels, torch copies and the NCCL calls are ordered on torch's current stream
-        self.r.set_stream(self.r.torch.cuda.current_stream().cuda_stream)
+        # kernels, torch copies and the NCCL calls are all ordered on ONE non-default torch stream
+        # (kamino_set_stream treats the NULL / legacy default stream as "use the context's own")
+        torch = self.r.torch
+        self.stream = torch.cuda.Stream(device=torch.device("cuda", device))
+        self.r.set_stream(self.stream.cuda_stream)
 
     def close(self):
         self.r.close()
 
     def step(self, nSteps=1):
+        with self.r.torch.cuda.stream(self.stream):
+            self._step(nSteps)
+
+    def sync(self):
+        self.stream.synchronize()
+
+    def _step(self, nSteps):
         r, dist = self.r, self.dist
         for _ in range(nSteps):
             if self.world > 1:

@@ -38,10 +38,10 @@ def main():
     s.r.solver.density.copyToGPU()
     dist.barrier(); torch.cuda.synchronize()
     s.step(2)                                           # warm-up (NCCL channels)
-    dist.barrier(); torch.cuda.synchronize()
+    s.sync(); dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     s.step(steps)
-    torch.cuda.synchronize(); dist.barrier()
+    s.sync(); torch.cuda.synchronize(); dist.barrier()
     el = time.perf_counter() - t0
     u, v, rho = s.r.download_band()
     parts = [None] * world
