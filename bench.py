@@ -210,6 +210,8 @@ def main():
     from kaminogpu_b200 import capi
     from kaminogpu_b200.solver import KaminoSolver
 
+    if os.environ.get("KAMINO_DEBUG_STEP_MASK"):
+        raise SystemExit("bench.py: KAMINO_DEBUG_STEP_MASK is set (timing instrumentation that skips kernels); refusing to run")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- kaminogpu_b200 has no CPU path")
     torch.cuda.set_device(local_rank)

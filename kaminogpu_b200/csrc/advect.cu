@@ -5,6 +5,7 @@
 // launches and two device syncs become ONE launch whose 1-D grid is partitioned into
 // four block ranges (u_phi cells | u_theta cells | density cells | particles). All four
 // read the pre-advection velocity, as in the reference.
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -147,7 +148,21 @@ advectKernel(GridParams g, AdvectArgs a)
                                                   tiles[0], tiles[1], tiles[2]);
         return;
     }
-    const long k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
+    long k;
+    if (a.latticeInner > 0) {
+        // compact patch of the particle lattice per warp / block (see AdvectArgs)
+        const int pb = block - a.tileBlocks;
+        const int blockO = pb / a.blocksInner, blockI = pb - blockO * a.blocksInner;
+        const int log2BI = a.log2Inner < 4 ? 4 : a.log2Inner;               // block patch: 2^log2BI rows
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int warpsInner = 1 << (log2BI - a.log2Inner);
+        const int wi = warp & (warpsInner - 1), wo = warp >> (log2BI - a.log2Inner);
+        const int inner = (blockI << log2BI) + (wi << a.log2Inner) + (lane & ((1 << a.log2Inner) - 1));
+        const int outer = blockO * (kAdvectThreads >> log2BI) + wo * (32 >> a.log2Inner) + (lane >> a.log2Inner);
+        k = (inner < a.latticeInner && outer < a.latticeOuter) ? (long)outer * a.latticeInner + inner : g.numParticles;
+    } else {
+        k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
+    }
     if (k < g.numParticles) {                       // the reference has no tail guard (:323)
         const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
         float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
@@ -199,8 +214,24 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
     // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget), default 5
     static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 5; }();
     a.tileBlocks = (g.nPhi / 32) * (g.rowCount / kTileRows);      // rowBegin, rowCount: multiples of kTileRows
-    const int blocksParticles = (a.particles && g.numParticles > 0)
+    int blocksParticles = (a.particles && g.numParticles > 0)
         ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
+    a.latticeInner = a.latticeOuter = a.log2Inner = a.blocksInner = 0;
+    static const int lattice = [] { const char* e = getenv("KAMINO_PARTICLE_TILES"); return e ? atoi(e) : 1; }();
+    if (blocksParticles > 0 && lattice) {
+        // numOfParticles = numTheta * (2 numTheta) for a seeded set (kernel/KaminoParticles.cu:22-25)
+        const long m = (long)(sqrt((double)g.numParticles / 2.0) + 0.5);
+        if (m >= 16 && 2 * m * m == g.numParticles) {
+            // warp patch height: about three grid cells of lattice rows (spacing nTheta / m cells)
+            int log2Inner = 2;
+            while (log2Inner < 5 && (2L << log2Inner) * g.nTheta <= 3 * m) ++log2Inner;
+            const int log2BI = log2Inner < 4 ? 4 : log2Inner;
+            a.latticeInner = (int)m; a.latticeOuter = (int)(2 * m); a.log2Inner = log2Inner;
+            a.blocksInner = (int)((m + (1 << log2BI) - 1) >> log2BI);
+            const int rowsOuter = kAdvectThreads >> log2BI;
+            blocksParticles = a.blocksInner * (int)((2 * m + rowsOuter - 1) / rowsOuter);
+        }
+    }
     dim3 grid(a.tileBlocks + blocksParticles, batch);
     switch (variant) {
     case 3: return launchChained(advectKernel<3>, grid, dim3(kAdvectThreads), 0, stream, g, a);

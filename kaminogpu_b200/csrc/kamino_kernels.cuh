@@ -22,6 +22,16 @@ struct AdvectArgs {
     const float* cofPhiTheta;
     const SamplerConsts* consts;  // device copy of the sampler constants (sampler.cuh)
     int tileBlocks;                              // filled by launchAdvect
+    // thread -> particle mapping of the particle blocks (filled by launchAdvect). A seeded particle
+    // set is a jittered numPhi x numTheta lattice stored phi-major (kernel/KaminoParticles.cu:39-62,
+    // index i * numTheta + j), so 32 consecutive particles lie on 32 different theta rows and every
+    // gather of a warp touches 32 cache lines. When the count has the lattice form 2 m^2 the warps
+    // are laid over compact patches of the lattice instead ((32 >> log2Inner) columns x
+    // (1 << log2Inner) rows per warp, 256 / blockInner x blockInner per block); any other count
+    // keeps the linear mapping (latticeInner = 0). The mapping never changes a result.
+    int latticeInner, latticeOuter;              // numTheta, numPhi of the lattice (0: linear mapping)
+    int log2Inner;                               // log2 of the warp patch height (rows of the lattice)
+    int blocksInner;                             // particle blocks along the inner (theta) dimension
 };
 
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
