@@ -31,33 +31,33 @@ constexpr int kAdvectThreads = 256;
 // One RK2 backtrace from the node of `KIND` cell (j, i); samples `src` at the foot point. The
 // two velocity samples of each stage are issued together. kernel/KaminoCore.cu:195-228
 // (and :240-273, :285-318); arithmetic notes below.
-template <int KIND>
+template <int KIND, bool SAFE>
 __device__ __forceinline__ float backtrace(const SamplerRegs& g, const SamplerConsts* __restrict__ sc, float cofTheta,
                                            const float* __restrict__ velPhi, const float* __restrict__ velTheta,
                                            const float* __restrict__ src, int i, int j, float cofPhi,
-                                           const float* tilePhi, const float* tileTheta, const float* tileSrc)
+                                           unsigned tilePhi, unsigned tileTheta, unsigned tileSrc)
 {
     const float offPhi = (KIND == kVPhi) ? -0.5f : 0.0f;
     const float offTheta = (KIND == kVTheta) ? 1.0f : 0.5f;
     const float gPhi = __fmul_rn(__fadd_rn((float)i, offPhi), g.h);
     const float gTheta = __fmul_rn(__fadd_rn((float)j, offTheta), g.h);
-    PendingSample pu = sampleIssue<kVPhi, true>(g, sc, velPhi, gPhi, gTheta, tilePhi);
-    PendingSample pv = sampleIssue<kVTheta, true>(g, sc, velTheta, gPhi, gTheta, tileTheta);
+    PendingSample pu = sampleIssueTiled<kVPhi, SAFE>(g, sc, velPhi, gPhi, gTheta, tilePhi);
+    PendingSample pv = sampleIssueTiled<kVTheta, SAFE>(g, sc, velTheta, gPhi, gTheta, tileTheta);
     const float guPhi = sampleFinish(pu);
     const float guTheta = sampleFinish(pv);
     const float deltaPhi = __fmul_rn(guPhi, cofPhi);
     const float deltaTheta = __fmul_rn(guTheta, cofTheta);
     const float midPhi = __fmaf_rn(-0.5f, deltaPhi, gPhi);
     const float midTheta = __fmaf_rn(-0.5f, deltaTheta, gTheta);
-    pu = sampleIssue<kVPhi, true>(g, sc, velPhi, midPhi, midTheta, tilePhi);
-    pv = sampleIssue<kVTheta, true>(g, sc, velTheta, midPhi, midTheta, tileTheta);
+    pu = sampleIssueTiled<kVPhi, SAFE>(g, sc, velPhi, midPhi, midTheta, tilePhi);
+    pv = sampleIssueTiled<kVTheta, SAFE>(g, sc, velTheta, midPhi, midTheta, tileTheta);
     const float muPhi = sampleFinish(pu);
     const float muTheta = sampleFinish(pv);
     const float averuPhi = __fmul_rn(0.5f, __fadd_rn(muPhi, guPhi));
     const float averuTheta = __fmul_rn(0.5f, __fadd_rn(muTheta, guTheta));
     const float pPhi = __fmaf_rn(-averuPhi, cofPhi, gPhi);
     const float pTheta = __fmaf_rn(-averuTheta, cofTheta, gTheta);
-    return sampleFinish(sampleIssue<KIND, true>(g, sc, src, pPhi, pTheta, tileSrc));
+    return sampleFinish(sampleIssueTiled<KIND, SAFE>(g, sc, src, pPhi, pTheta, tileSrc));
 }
 
 // Arithmetic notes for backtrace():
@@ -111,11 +111,20 @@ advectKernel(GridParams g, AdvectArgs a)
     const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
     const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
     const SamplerRegs sr(a.consts);            // read-only table: independent of the previous kernel
-    const int block = blockIdx.x;
+    int block = blockIdx.x;
+    bool isTile = block < a.tileBlocks;
+    int particleBlock = block - a.tileBlocks;
+    if (a.mixStep) {
+        const unsigned q0 = (unsigned)(((unsigned long long)block * a.mixStep) >> 32);
+        const unsigned q1 = (unsigned)(((unsigned long long)(block + 1) * a.mixStep) >> 32);
+        isTile = q1 > q0;
+        particleBlock = block - (int)q0;
+        block = (int)q0;
+    }
     pdlWait();
 
-    if (block < a.tileBlocks) {
-        __shared__ float tiles[3][kTileH * kTileW];
+    if (isTile) {
+        __shared__ __align__(16) float tiles[3][kTileH * kTileW];
         const float* density = pinPointer(a.density + (size_t)sim * g.cells);
         const int log2TilesX = g.log2NPhi - 5;
         const int i0 = (block & ((1 << log2TilesX) - 1)) << 5;
@@ -123,35 +132,53 @@ advectKernel(GridParams g, AdvectArgs a)
         SamplerRegs tr = sr;
         tr.tileRow0 = j0 - 2;
         tr.tileCol0 = i0 - 4;
-        // stage the neighbourhood of the block's cells (rows clamped into the arrays: clamped rows
+        // stage the neighbourhood of the block's cells as float4 (tileCol0 is a multiple of 4, so a
+        // group of four columns never straddles the seam; rows clamped into the arrays: clamped rows
         // are never addressed by an interior sample; columns wrap around the seam)
-        for (int e = threadIdx.x; e < kTileH * kTileW; e += kAdvectThreads) {
-            const int r = e / kTileW, c = e - r * kTileW;
-            const int col = (tr.tileCol0 + c) & sr.mask;
-            const int row = min(max(tr.tileRow0 + r, 0), sr.nTheta - 1);
-            const int rowV = min(row, sr.nTheta - 2);
-            tiles[0][e] = __ldg(velPhi + (row * sr.N + col));
-            tiles[1][e] = __ldg(velTheta + (rowV * sr.N + col));
-            tiles[2][e] = __ldg(density + (row * sr.N + col));
+        constexpr int kVecPerRow = kTileW / 4, kVecPerTile = kTileH * kVecPerRow;
+        for (int e = threadIdx.x; e < 3 * kVecPerTile; e += kAdvectThreads) {
+            const int f = e / kVecPerTile, rem = e - f * kVecPerTile;
+            const int r = rem / kVecPerRow, q = rem - r * kVecPerRow;
+            const int col = (tr.tileCol0 + 4 * q) & sr.mask;
+            const int rowC = min(max(tr.tileRow0 + r, 0), sr.nTheta - 1);
+            const int row = (f == 1) ? min(rowC, sr.nTheta - 2) : rowC;
+            const float* src = (f == 0) ? velPhi : (f == 1) ? velTheta : density;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (row * sr.N + col)));
+            *reinterpret_cast<float4*>(&tiles[f][r * kTileW + 4 * q]) = v;
         }
         __syncthreads();
+        unsigned tileBase = (unsigned)__cvta_generic_to_shared(&tiles[0][0]);
+        asm volatile("" : "+r"(tileBase));       // opaque: kept in a register instead of re-derived per sample
+        const unsigned tPhi = tileBase, tTheta = tileBase + kTileBytes, tRho = tileBase + 2 * kTileBytes;
         const int i = i0 + (threadIdx.x & 31);
         const int j = j0 + (threadIdx.x >> 5);
         const size_t cell = (size_t)sim * g.cells + (size_t)j * g.nPhi + i;
         const float cofCentred = __ldg(a.cofPhiCentred + j);
-        a.velPhiOut[cell] = backtrace<kVPhi>(tr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred,
-                                             tiles[0], tiles[1], tiles[0]);
-        if (j < g.nTheta - 1)
-            a.velThetaOut[cell] = backtrace<kVTheta>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
-                                                     __ldg(a.cofPhiTheta + j), tiles[0], tiles[1], tiles[1]);
-        a.densityOut[cell] = backtrace<kCentered>(tr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j, cofCentred,
-                                                  tiles[0], tiles[1], tiles[2]);
+        // blocks whose tile lies inside rows [2, nTheta-4] and columns [2, N-2]: see sampleIssueTiled
+        const bool safe = tr.tileRow0 >= 2 && tr.tileRow0 + (kTileH - 1) <= sr.nTheta - 4
+                       && tr.tileCol0 >= 2 && tr.tileCol0 + (kTileW - 1) <= sr.N - 2;
+        if (safe) {
+            a.velPhiOut[cell] = backtrace<kVPhi, true>(tr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred,
+                                                       tPhi, tTheta, tPhi);
+            a.velThetaOut[cell] = backtrace<kVTheta, true>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
+                                                           __ldg(a.cofPhiTheta + j), tPhi, tTheta, tTheta);
+            a.densityOut[cell] = backtrace<kCentered, true>(tr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j,
+                                                            cofCentred, tPhi, tTheta, tRho);
+        } else {
+            a.velPhiOut[cell] = backtrace<kVPhi, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred,
+                                                        tPhi, tTheta, tPhi);
+            if (j < g.nTheta - 1)
+                a.velThetaOut[cell] = backtrace<kVTheta, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
+                                                                __ldg(a.cofPhiTheta + j), tPhi, tTheta, tTheta);
+            a.densityOut[cell] = backtrace<kCentered, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j,
+                                                             cofCentred, tPhi, tTheta, tRho);
+        }
         return;
     }
     long k;
     if (a.latticeInner > 0) {
         // compact patch of the particle lattice per warp / block (see AdvectArgs)
-        const int pb = block - a.tileBlocks;
+        const int pb = particleBlock;
         const int blockO = pb / a.blocksInner, blockI = pb - blockO * a.blocksInner;
         const int log2BI = a.log2Inner < 4 ? 4 : a.log2Inner;               // block patch: 2^log2BI rows
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,7 +188,7 @@ advectKernel(GridParams g, AdvectArgs a)
         const int outer = blockO * (kAdvectThreads >> log2BI) + wo * (32 >> a.log2Inner) + (lane >> a.log2Inner);
         k = (inner < a.latticeInner && outer < a.latticeOuter) ? (long)outer * a.latticeInner + inner : g.numParticles;
     } else {
-        k = (long)(block - a.tileBlocks) * kAdvectThreads + threadIdx.x;
+        k = (long)particleBlock * kAdvectThreads + threadIdx.x;
     }
     if (k < g.numParticles) {                       // the reference has no tail guard (:323)
         const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
@@ -226,11 +253,19 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
             int log2Inner = 2;
             while (log2Inner < 5 && (2L << log2Inner) * g.nTheta <= 3 * m) ++log2Inner;
             const int log2BI = log2Inner < 4 ? 4 : log2Inner;
+            if (log2Inner < 5) {       // a 32-row patch is the linear mapping (dense particle sets, r01g A/B at C1)
             a.latticeInner = (int)m; a.latticeOuter = (int)(2 * m); a.log2Inner = log2Inner;
             a.blocksInner = (int)((m + (1 << log2BI) - 1) >> log2BI);
             const int rowsOuter = kAdvectThreads >> log2BI;
             blocksParticles = a.blocksInner * (int)((2 * m + rowsOuter - 1) / rowsOuter);
+            }
         }
+    }
+    static const int mix = [] { const char* e = getenv("KAMINO_ADVECT_MIX"); return e ? atoi(e) : 1; }();
+    a.mixStep = 0;
+    if (mix && blocksParticles > 0 && a.tileBlocks > 0) {
+        const unsigned long long total = (unsigned long long)a.tileBlocks + blocksParticles;
+        a.mixStep = (((unsigned long long)a.tileBlocks << 32) + total - 1) / total;
     }
     dim3 grid(a.tileBlocks + blocksParticles, batch);
     switch (variant) {

@@ -237,11 +237,72 @@ struct PendingSample { float v00, v01, v10, v11, alphaPhi, alphaTheta; };
 
 constexpr int kTileH = 13;      // 8 rows of cells + 2 above + 3 below
 constexpr int kTileW = 40;      // 32 columns + 4 left + 4 right
+constexpr int kTileBytes = kTileH * kTileW * 4;
 
-template <int KIND, bool TILED = false>
+// The four corners of a cell from a shared-memory tile addressed by its 32-bit shared-window
+// address: explicit ld.shared with immediate offsets, so the tile base lives in one register for
+// the whole kernel (with generic pointers ptxas re-materialised the shared-window base -- S2UR,
+// UMOV, ULEA -- at every one of the 15 samples of a cell, r01f SASS profile).
+__device__ __forceinline__ void loadTileCell(unsigned addr, PendingSample& p)
+{
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p.v00) : "r"(addr));
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(p.v01) : "r"(addr));
+    asm volatile("ld.shared.f32 %0, [%1+160];" : "=f"(p.v10) : "r"(addr));
+    asm volatile("ld.shared.f32 %0, [%1+164];" : "=f"(p.v11) : "r"(addr));
+    static_assert(kTileW * 4 == 160, "immediate offsets above assume 40-column tiles");
+}
+
+// Sample from the block's tile (tile blocks of the advection kernel). `tile` is the shared-window
+// address of the field's kTileH x kTileW tile. Everything that is not served by the tile goes to
+// the general path out of line (polar rows, whose phi displacement exceeds the halo).
+//   SAFE = false: the interior test on the coordinates plus the tile test on the indices.
+//   SAFE = true : blocks whose tile lies inside rows [2, nTheta-4] and columns [2, N-2] (all but the
+//     first / last tile row and column of the grid). There the tile test alone implies the interior
+//     test: thetaIndex in [2, nTheta-4] means RN(theta * invH) in [2, nTheta-3), hence
+//     1.5 h <= theta < (lastRow - 0.5) h for either lastRow, and likewise 1.5 h <= phi < 2 pi
+//     (NaN / inf convert to indices that fail the test). Lanes that pass run the same fast-path
+//     arithmetic as before, all others the general path: no result changes, five instructions per
+//     sample disappear.
+template <int KIND, bool SAFE>
+__device__ __forceinline__ PendingSample sampleIssueTiled(const SamplerRegs& g, const SamplerConsts* __restrict__ consts,
+                                                          const float* __restrict__ field, float phiRaw, float thetaRaw,
+                                                          unsigned tile)
+{
+    const float phi = (KIND == kVPhi) ? __fadd_rn(phiRaw, g.halfH) : phiRaw;
+    const float theta = (KIND == kVTheta) ? __fsub_rn(thetaRaw, g.h) : __fsub_rn(thetaRaw, g.halfH);
+    const float normedPhi = __fmul_rn(phi, g.invH);
+    const float normedTheta = __fmul_rn(theta, g.invH);
+    const int phiIndex = (int)floorf(normedPhi);
+    const int thetaIndex = (int)floorf(normedTheta);
+    const int tr = thetaIndex - g.tileRow0;
+    int tc;
+    bool ok;
+    if (SAFE) {
+        tc = phiIndex - g.tileCol0;
+        ok = (unsigned)tr < (unsigned)(kTileH - 1) && (unsigned)tc < (unsigned)(kTileW - 1);
+    } else {
+        const unsigned thetaSpan = (KIND == kVTheta) ? g.thetaSpanVTheta : g.thetaSpanCentred;
+        const bool interior = (__float_as_uint(theta) - g.thetaLoBits) < thetaSpan
+                           && (__float_as_uint(phi) - g.phiLoBits) < g.phiSpan;
+        tc = (phiIndex - g.tileCol0) & g.mask;
+        ok = interior && (unsigned)tr < (unsigned)(kTileH - 1) && (unsigned)tc < (unsigned)(kTileW - 1);
+    }
+    PendingSample p;
+    if (ok) {
+        p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
+        p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
+        loadTileCell(tile + 4u * (unsigned)(tr * kTileW + tc), p);
+    } else {
+        const float v = sampleGeneral<KIND>(consts, field, phiRaw, thetaRaw);
+        p.v00 = p.v01 = p.v10 = p.v11 = v;
+        p.alphaPhi = p.alphaTheta = 0.0f;
+    }
+    return p;
+}
+
+template <int KIND>
 __device__ __forceinline__ PendingSample sampleIssue(const SamplerRegs& g, const SamplerConsts* __restrict__ consts,
-                                                     const float* __restrict__ field, float phiRaw, float thetaRaw,
-                                                     const float* tile = nullptr)
+                                                     const float* __restrict__ field, float phiRaw, float thetaRaw)
 {
     const float phi = (KIND == kVPhi) ? __fadd_rn(phiRaw, g.halfH) : phiRaw;
     const float theta = (KIND == kVTheta) ? __fsub_rn(thetaRaw, g.h) : __fsub_rn(thetaRaw, g.halfH);
@@ -249,29 +310,7 @@ __device__ __forceinline__ PendingSample sampleIssue(const SamplerRegs& g, const
     const bool interior = (__float_as_uint(theta) - g.thetaLoBits) < thetaSpan
                        && (__float_as_uint(phi) - g.phiLoBits) < g.phiSpan;
     PendingSample p;
-    if (TILED) {
-        // tile blocks: everything that is not served by the tile goes to the general path out of
-        // line (polar rows, whose phi displacement exceeds the halo), which keeps this path short
-        const float normedPhi = __fmul_rn(phi, g.invH);
-        const float normedTheta = __fmul_rn(theta, g.invH);
-        const int phiIndex = (int)floorf(normedPhi);
-        const int thetaIndex = (int)floorf(normedTheta);
-        const int tr = thetaIndex - g.tileRow0;
-        const int tc = (phiIndex - g.tileCol0) & g.mask;
-        if (interior && (unsigned)tr < (unsigned)(kTileH - 1) && (unsigned)tc < (unsigned)(kTileW - 1)) {
-            p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
-            p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
-            const float* t = tile + (tr * kTileW + tc);
-            p.v00 = t[0];
-            p.v01 = t[1];
-            p.v10 = t[kTileW];
-            p.v11 = t[kTileW + 1];
-        } else {
-            const float v = sampleGeneral<KIND>(consts, field, phiRaw, thetaRaw);
-            p.v00 = p.v01 = p.v10 = p.v11 = v;
-            p.alphaPhi = p.alphaTheta = 0.0f;
-        }
-    } else if (interior) {
+    if (interior) {
         const float normedPhi = __fmul_rn(phi, g.invH);
         const float normedTheta = __fmul_rn(theta, g.invH);
         const int phiIndex = (int)floorf(normedPhi);

@@ -1,12 +1,12 @@
 #!/bin/bash
-# A/B of environment switches on the C2 / C3 bench lines.  gpurun -- 'bash scripts/gpu_ab.sh tag "VAR=a VAR=b ..." [workloads]'
+# A/B of environment switches (VAR=a, or VAR1=a,VAR2=b for combinations) on the C2 / C3 bench lines.  gpurun -- 'bash scripts/gpu_ab.sh tag "VAR=a VAR=b ..." [workloads]'
 TAG=${1:-ab}; VARIANTS=${2:-"KAMINO_FORK=0 KAMINO_FORK=1"}; WL=${3:-"c2 c3"}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 for v in $VARIANTS; do
   for w in $WL; do
     steps=1000; [ $w = c3 ] && steps=100
-    env $v timeout 600 python bench.py --workload $w --steps $steps --warmup 10 --no-cpu-baseline > $OUT/bench_${w}_$v.json 2> $OUT/bench_${w}_$v.err
+    env $(echo $v | tr "," " ") timeout 600 python bench.py --workload $w --steps $steps --warmup 10 --no-cpu-baseline > $OUT/bench_${w}_$v.json 2> $OUT/bench_${w}_$v.err
     python - <<PY
 import json
 try:
