@@ -105,8 +105,9 @@ int kamino_upload_particles_async(kamino_ctx* ctx, int sim, const float* pinnedH
 
 /* KaminoQuantity::getGPUThisStep / getGPUNextStep / get*PitchInElements
  * (include/KaminoQuantity.cuh:60-66): raw device pointer of the current this/next buffer
- * (which = 0 / 1) and its pitch in elements. The pointers swap after every phase exactly
- * as the reference's do. */
+ * (which = 0 / 1) and its pitch in elements. The roles move after every phase as the
+ * reference's swaps do (the velocity rotates through three buffers instead of two, so
+ * re-query the pointers after a phase rather than swapping a cached pair). */
 int kamino_field_device_ptr(kamino_ctx* ctx, int field, int sim, int which,
                             void** devicePtr, size_t* pitchInElements);
 /* KaminoParticles::coordGPUThisStep / coordGPUNextStep (include/KaminoParticles.cuh:18-19). */
@@ -169,12 +170,16 @@ int kamino_run_frames(kamino_ctx* ctx, int nFrames, int stepsPerFrame,
  * are not split by phase). */
 int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, float* projection, int reset);
 
-/* Number of kernel launches one kamino_step(ctx, 1) performs (for bench.py's gpu_launches). */
+/* Number of kernel launches one kamino_step(ctx, 1) performs (for bench.py's gpu_launches):
+ * 5, or 6 when the context holds particles and they run as their own kernel on a parallel
+ * branch of the step graph (the default; KAMINO_FORK_PARTICLES=0 fuses them into the
+ * advection launch). */
 int kamino_launches_per_step(const kamino_ctx* ctx);
 
 /* Run nSteps steps with every kernel launched individually and bracketed by CUDA events on
  * the context's stream; kernelSeconds[k] (k = 0 .. kamino_launches_per_step()-1: advection,
- * geometric, divergence+FFT, tridiagonal, inverse FFT+gradient) receives the summed device
+ * geometric, divergence+FFT, tridiagonal, inverse FFT+gradient, then the particle kernel if
+ * there is one) receives the summed device
  * time of kernel k. The per-kernel counterpart of the reference's per-phase KaminoTimer
  * brackets (kernel/KaminoSolver.cu:201-218). Synchronous. */
 int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds);

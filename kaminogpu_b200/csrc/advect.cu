@@ -71,17 +71,25 @@ __device__ __forceinline__ float backtrace(const SamplerRegs& g, const SamplerCo
 // Tried and rejected (r01g/r01h A/B): advancing the three backtraces of a cell stage by stage so
 // that six samples are in flight per round -- 80-100 registers, 10 % slower than this form.
 
-// kernel/KaminoCore.cu:321-342
-__device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, const SamplerConsts* __restrict__ sc,
-                                               float radius, float dt, float cofTheta,
-                                               const float* __restrict__ velPhi,
-                                               const float* __restrict__ velTheta, float2 pos)
+// kernel/KaminoCore.cu:321-342, in two halves so that a thread can have the gathers of several
+// particles in flight: the two velocity samples are issued, then finished and applied.
+struct PendingParticle { PendingSample u, v; };
+
+__device__ __forceinline__ PendingParticle particleIssue(const SamplerRegs& g, const SamplerConsts* __restrict__ sc,
+                                                         const float* __restrict__ velPhi,
+                                                         const float* __restrict__ velTheta, float2 pos)
+{
+    PendingParticle p;
+    p.u = sampleIssue<kVPhi>(g, sc, velPhi, pos.x, pos.y);
+    p.v = sampleIssue<kVTheta>(g, sc, velTheta, pos.x, pos.y);
+    return p;
+}
+
+__device__ __forceinline__ float2 particleFinish(float radius, float dt, float cofTheta, float2 pos, const PendingParticle& p)
 {
     const float posPhi = pos.x, posTheta = pos.y;
-    const PendingSample pu = sampleIssue<kVPhi>(g, sc, velPhi, posPhi, posTheta);
-    const PendingSample pv = sampleIssue<kVTheta>(g, sc, velTheta, posPhi, posTheta);
-    const float uPhi = sampleFinish(pu);
-    const float uTheta = sampleFinish(pv);
+    const float uPhi = sampleFinish(p.u);
+    const float uTheta = sampleFinish(p.v);
     const float latRadius = __fmul_rn(radius, sinf(posTheta));
     const float cofPhi = __fdiv_rn(dt, latRadius);
     float updatedTheta = __fmaf_rn(uTheta, cofTheta, posTheta);
@@ -92,6 +100,14 @@ __device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, const Sampl
         updatedPhi = v.phi; updatedTheta = v.theta;
     }
     return make_float2(updatedPhi, updatedTheta);
+}
+
+__device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, const SamplerConsts* __restrict__ sc,
+                                               float radius, float dt, float cofTheta,
+                                               const float* __restrict__ velPhi,
+                                               const float* __restrict__ velTheta, float2 pos)
+{
+    return particleFinish(radius, dt, cofTheta, pos, particleIssue(g, sc, velPhi, velTheta, pos));
 }
 
 // Grid: [tile blocks | particle blocks] x batch. A tile block owns kTileRows x 32 cells (one warp
@@ -197,6 +213,41 @@ advectKernel(GridParams g, AdvectArgs a)
     }
 }
 
+// The tracer particles as a kernel of their own (forked mode: it runs on a parallel branch of the
+// step graph, next to the kernels of the velocity chain). The path is bound by memory latency --
+// position load, then eight dependent gathers, then the store (r01g: 1.2-1.5 TB/s with one
+// particle per thread at 40 warps per SM) -- so every thread owns kParticlesPerThread particles,
+// kAdvectThreads apart (coalesced), loads all positions first, issues all gathers, then finishes.
+constexpr int kParticlesPerThread = 2;
+
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(kAdvectThreads, MINBLOCKS)
+advectParticlesKernel(GridParams g, AdvectArgs a)
+{
+    const int sim = blockIdx.y;
+    const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
+    const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
+    const SamplerRegs sr(a.consts);
+    const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
+    float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
+    const long base = (long)blockIdx.x * (kAdvectThreads * kParticlesPerThread) + threadIdx.x;
+    float2 pos[kParticlesPerThread];
+#pragma unroll
+    for (int m = 0; m < kParticlesPerThread; ++m) {
+        const long k = base + m * kAdvectThreads;
+        pos[m] = (k < g.numParticles) ? __ldcs(in + k) : make_float2(1.0f, 1.0f);
+    }
+    PendingParticle pending[kParticlesPerThread];
+#pragma unroll
+    for (int m = 0; m < kParticlesPerThread; ++m) pending[m] = particleIssue(sr, a.consts, velPhi, velTheta, pos[m]);
+#pragma unroll
+    for (int m = 0; m < kParticlesPerThread; ++m) {
+        const long k = base + m * kAdvectThreads;
+        const float2 next = particleFinish(g.radius, g.dt, g.cofTheta, pos[m], pending[m]);
+        if (k < g.numParticles) __stcs(out + k, next);     // the reference has no tail guard (:323)
+    }
+}
+
 template <int KIND>
 __global__ void locateKernel(const SamplerConsts* __restrict__ consts, long n, const float* __restrict__ phiRaw,
                              const float* __restrict__ thetaRaw, int* phiIndex, int* thetaIndex,
@@ -261,7 +312,7 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
             }
         }
     }
-    static const int mix = [] { const char* e = getenv("KAMINO_ADVECT_MIX"); return e ? atoi(e) : 1; }();
+    static const int mix = [] { const char* e = getenv("KAMINO_ADVECT_MIX"); return e ? atoi(e) : 0; }();
     a.mixStep = 0;
     if (mix && blocksParticles > 0 && a.tileBlocks > 0) {
         const unsigned long long total = (unsigned long long)a.tileBlocks + blocksParticles;
@@ -274,6 +325,18 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
     case 6: return launchChained(advectKernel<6>, grid, dim3(kAdvectThreads), 0, stream, g, a);
     default: return launchChained(advectKernel<5>, grid, dim3(kAdvectThreads), 0, stream, g, a);
     }
+}
+
+cudaError_t launchAdvectParticles(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
+{
+    if (!a.particles || g.numParticles <= 0) return cudaSuccess;
+    const long perBlock = (long)kAdvectThreads * kParticlesPerThread;
+    dim3 grid((unsigned)((g.numParticles + perBlock - 1) / perBlock), batch);
+    // experiment switch: KAMINO_PARTICLE_BLOCKS = 3 (76 registers, no spills) | 4 (64 registers)
+    static const int minBlocks = [] { const char* e = getenv("KAMINO_PARTICLE_BLOCKS"); return e ? atoi(e) : 3; }();
+    if (minBlocks == 4) advectParticlesKernel<4><<<grid, kAdvectThreads, 0, stream>>>(g, a);
+    else advectParticlesKernel<3><<<grid, kAdvectThreads, 0, stream>>>(g, a);
+    return cudaGetLastError();
 }
 
 cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const float* phiRaw, const float* thetaRaw,

@@ -1,14 +1,15 @@
 // Context, memory layout, step graphs and the C ABI of kamino_b200 (include/kamino_b200.h).
 //
 // HBM layout (one arena per context, every sub-buffer 256-byte aligned, batch-major):
-//   velPhi[2], velTheta[2], density[2]   batch x nTheta x nPhi fp32 each (u_theta uses
-//                                        nTheta-1 rows of its slot), double-buffered
+//   velPhi[3], velTheta[3], density[2]   batch x nTheta x nPhi fp32 each (u_theta uses
+//                                        nTheta-1 rows of its slot); density is double-buffered,
+//                                        the velocity rotates through three buffers (see below)
 //   pressure                             batch x nTheta x nPhi fp32
 //   spectrum                             batch x nTheta x nPhi/2 float2 (half spectrum)
 //   particles[2]                         batch x numParticles float2, double-buffered
 //   tables                               twiddles + per-row constants + the LU factors of every
 //                                        wavenumber's theta system (10 B per cell, read-only)
-// = 36 B/cell of state + 10 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
+// = 44 B/cell of state + 10 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
 // SURVEY.md appendix B).
 #include <cstdio>
 #include <cstdlib>
@@ -30,13 +31,14 @@ struct kamino_ctx {
     GridParams g{};
     cudaStream_t ownStream = nullptr;    // graphs are captured here
     cudaStream_t copyStream = nullptr;   // frame read-backs
+    cudaStream_t sideStream = nullptr;   // particle branch of the step graph (lower priority)
     cudaStream_t stream = nullptr;       // where work is launched (ownStream unless overridden)
     char* arena = nullptr;          // fields, spectrum, tables
     size_t arenaBytes = 0;
     char* particleArena = nullptr;  // particles[2] + read-back snapshot (sized by kamino_alloc_particles)
 
-    float* velPhi[2]{};
-    float* velTheta[2]{};
+    float* velPhi[3]{};
+    float* velTheta[3]{};
     float* density[2]{};
     float* pressure = nullptr;
     float2* spectrum = nullptr;
@@ -46,10 +48,19 @@ struct kamino_ctx {
     SpectralTables tables{};
 
     int velIdx = 0, densityIdx = 0, particleIdx = 0;   // which buffer is "this step"
+    // Velocity buffers in rotation. advect writes next(v), geometric writes next(next(v)), the
+    // projection corrects that buffer in place. With three buffers the pre-advection velocity of
+    // step n stays untouched until advect of step n+1, so the tracer particles of step n (which read
+    // only that velocity, kernel/KaminoCore.cu:376-381) run as their own kernel on a parallel
+    // branch of the step graph, in the shadow of the latency-bound geometric and projection
+    // kernels. KAMINO_FORK_PARTICLES=0 restores two buffers and the fused advection launch.
+    int velBuffers = 3;
+    bool forkParticles = true;
 
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (parity, steps) -> exec
 
     cudaEvent_t evStart = nullptr, evStop = nullptr, evSnap = nullptr, evCopied = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     float advectionTime = 0.f, geometricTime = 0.f, projectionTime = 0.f;
 
     std::string lastError;
@@ -57,7 +68,10 @@ struct kamino_ctx {
 
 namespace {
 
-constexpr int kStepKernels = 5;
+constexpr int kStepKernels = 5;      // + 1 (the particle kernel) when the particles run on their own branch
+
+int nextVel(const kamino_ctx* ctx, int v) { return (v + 1) % ctx->velBuffers; }
+bool particlesForked(const kamino_ctx* ctx) { return ctx->forkParticles && ctx->g.numParticles > 0; }
 
 thread_local std::string g_createError;
 
@@ -94,8 +108,8 @@ size_t fieldRows(const kamino_ctx* ctx, int field)
 float* fieldBuffer(kamino_ctx* ctx, int field, int which)
 {
     switch (field) {
-    case KAMINO_VEL_PHI: return ctx->velPhi[ctx->velIdx ^ which];
-    case KAMINO_VEL_THETA: return ctx->velTheta[ctx->velIdx ^ which];
+    case KAMINO_VEL_PHI: return ctx->velPhi[which ? nextVel(ctx, ctx->velIdx) : ctx->velIdx];
+    case KAMINO_VEL_THETA: return ctx->velTheta[which ? nextVel(ctx, ctx->velIdx) : ctx->velIdx];
     case KAMINO_DENSITY: return ctx->density[ctx->densityIdx ^ which];
     case KAMINO_PRESSURE: return ctx->pressure;
     default: return nullptr;
@@ -112,8 +126,8 @@ AdvectArgs advectArgs(kamino_ctx* ctx, const IndexState& st)
     a.velTheta = ctx->velTheta[st.vel];
     a.density = ctx->density[st.density];
     a.particles = ctx->g.numParticles > 0 ? ctx->particles[st.particle] : nullptr;
-    a.velPhiOut = ctx->velPhi[st.vel ^ 1];
-    a.velThetaOut = ctx->velTheta[st.vel ^ 1];
+    a.velPhiOut = ctx->velPhi[nextVel(ctx, st.vel)];
+    a.velThetaOut = ctx->velTheta[nextVel(ctx, st.vel)];
     a.densityOut = ctx->density[st.density ^ 1];
     a.particlesOut = ctx->g.numParticles > 0 ? ctx->particles[st.particle ^ 1] : nullptr;
     a.cofPhiCentred = ctx->tables.cofPhiCentred;
@@ -122,18 +136,27 @@ AdvectArgs advectArgs(kamino_ctx* ctx, const IndexState& st)
     return a;
 }
 
+// the particle kernel of the forked mode (reads the pre-advection velocity st.vel); does not touch `st`
+cudaError_t enqueueParticles(kamino_ctx* ctx, const IndexState& st, cudaStream_t s)
+{
+    return launchAdvectParticles(ctx->g, advectArgs(ctx, st), ctx->batch, s);
+}
+
+// cells (and, unless the particles run as their own kernel, the particles); flips the indices
 cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
-    cudaError_t e = launchAdvect(ctx->g, advectArgs(ctx, st), ctx->batch, s);
-    st.vel ^= 1; st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
+    AdvectArgs a = advectArgs(ctx, st);
+    if (particlesForked(ctx)) { a.particles = nullptr; a.particlesOut = nullptr; }
+    cudaError_t e = launchAdvect(ctx->g, a, ctx->batch, s);
+    st.vel = nextVel(ctx, st.vel); st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
     return e;
 }
 
 cudaError_t enqueueGeometric(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
     cudaError_t e = launchGeometric(ctx->g, ctx->tables, ctx->velPhi[st.vel], ctx->velTheta[st.vel],
-                                    ctx->velPhi[st.vel ^ 1], ctx->velTheta[st.vel ^ 1], ctx->batch, s);
-    st.vel ^= 1;                                          // kernel/KaminoCore.cu:582
+                                    ctx->velPhi[nextVel(ctx, st.vel)], ctx->velTheta[nextVel(ctx, st.vel)], ctx->batch, s);
+    st.vel = nextVel(ctx, st.vel);                        // kernel/KaminoCore.cu:582
     return e;
 }
 
@@ -164,6 +187,7 @@ cudaError_t enqueueProject(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 }
 
 // kernel k of a step: 0 advect, 1 geometric, 2 divergence+FFT, 3 tridiagonal, 4 inverse FFT+gradient
+// (the particle kernel of the forked mode is enqueued by the callers, before kernel 0)
 cudaError_t enqueueStepKernel(kamino_ctx* ctx, IndexState& st, int k, cudaStream_t s)
 {
     if (k == 0) return enqueueAdvect(ctx, st, s);
@@ -172,32 +196,31 @@ cudaError_t enqueueStepKernel(kamino_ctx* ctx, IndexState& st, int k, cudaStream
 }
 
 // Timing instrumentation only (scripts/step_mask_timing.py): KAMINO_DEBUG_STEP_MASK leaves kernels
-// out of the captured step graph (bit k = kernel k) to attribute the in-graph step time; the
-// results of such a run are meaningless and bench.py refuses to run with it set.
+// out of the captured step graph (bit k = kernel k, bit 5 = the particle kernel of the forked mode)
+// to attribute the in-graph step time; the results of such a run are meaningless and bench.py
+// refuses to run with it set.
 int debugStepMask()
 {
-    static const int mask = [] { const char* e = getenv("KAMINO_DEBUG_STEP_MASK"); return e ? atoi(e) : 31; }();
+    static const int mask = [] { const char* e = getenv("KAMINO_DEBUG_STEP_MASK"); return e ? atoi(e) : 63; }();
     return mask;
 }
 
+// kernel k of a step unless the instrumentation mask leaves it out (the buffer roles still move)
+cudaError_t enqueueStepKernelMasked(kamino_ctx* ctx, IndexState& st, int k, cudaStream_t s)
+{
+    if (debugStepMask() & (1 << k)) return enqueueStepKernel(ctx, st, k, s);
+    if (k == 0) { st.vel = nextVel(ctx, st.vel); st.density ^= 1; st.particle ^= 1; }
+    else if (k == 1) st.vel = nextVel(ctx, st.vel);
+    return cudaSuccess;
+}
+
+// one step in stream order (phase-style): the particle kernel of the forked mode first
 cudaError_t enqueueStep(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
-    const int mask = debugStepMask();
-    if (mask != 31) {
-        for (int k = 0; k < 5; ++k) {
-            if (mask & (1 << k)) {
-                cudaError_t e = enqueueStepKernel(ctx, st, k, s);
-                if (e != cudaSuccess) return e;
-            } else if (k == 0) { st.vel ^= 1; st.density ^= 1; st.particle ^= 1; }
-            else if (k == 1) { st.vel ^= 1; }
-        }
-        return cudaSuccess;
-    }
-    cudaError_t e = enqueueAdvect(ctx, st, s);
-    if (e != cudaSuccess) return e;
-    e = enqueueGeometric(ctx, st, s);
-    if (e != cudaSuccess) return e;
-    return enqueueProject(ctx, st, s);
+    cudaError_t e = cudaSuccess;
+    if (particlesForked(ctx) && (debugStepMask() & 32)) e = enqueueParticles(ctx, st, s);
+    for (int k = 0; k < kStepKernels && e == cudaSuccess; ++k) e = enqueueStepKernelMasked(ctx, st, k, s);
+    return e;
 }
 
 void dropGraphs(kamino_ctx* ctx)
@@ -210,7 +233,7 @@ void dropGraphs(kamino_ctx* ctx)
 // returns to its starting value after every step; density and particles flip once per step.
 int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
 {
-    const int roles = (ctx->velIdx << 2) | (ctx->densityIdx << 1) | ctx->particleIdx;
+    const int roles = (ctx->velIdx << 2) | (ctx->densityIdx << 1) | ctx->particleIdx;   // velIdx: 0 .. velBuffers-1
     auto key = std::make_pair(roles, steps);
     auto it = ctx->graphs.find(key);
     if (it != ctx->graphs.end()) { *out = it->second; return 0; }
@@ -219,7 +242,28 @@ int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
     KB_TRY(ctx, cudaStreamBeginCapture(ctx->ownStream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
     pdlSetCapturing(true);
-    for (int k = 0; k < steps && e == cudaSuccess; ++k) e = enqueueStep(ctx, st, ctx->ownStream);
+    static const bool sequential = [] { const char* e = getenv("KAMINO_FORK_SEQUENTIAL"); return e && atoi(e) != 0; }();
+    const bool fork = particlesForked(ctx) && (debugStepMask() & 32) && !sequential;   // KAMINO_FORK_SEQUENTIAL=1: A/B switch
+    for (int k = 0; k < steps && e == cudaSuccess; ++k) {
+        if (fork) {
+            // parallel branch: particles of this step on the side stream, joined before the next
+            // step's advection overwrites the velocity buffer they read
+            e = cudaEventRecord(ctx->evFork, ctx->ownStream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sideStream, ctx->evFork, 0);
+            pdlSetCapturing(false);
+            if (e == cudaSuccess) e = enqueueParticles(ctx, st, ctx->sideStream);
+            pdlSetCapturing(true);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->evJoin, ctx->sideStream);
+            // the first kernel after a join has two predecessors: launched without the programmatic edge
+            if (k > 0) pdlSetCapturing(false);
+            if (e == cudaSuccess) e = enqueueStepKernelMasked(ctx, st, 0, ctx->ownStream);
+            pdlSetCapturing(true);
+            for (int q = 1; q < kStepKernels && e == cudaSuccess; ++q) e = enqueueStepKernelMasked(ctx, st, q, ctx->ownStream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->ownStream, ctx->evJoin, 0);
+        } else {
+            e = enqueueStep(ctx, st, ctx->ownStream);
+        }
+    }
     pdlSetCapturing(false);
     cudaError_t e2 = cudaStreamEndCapture(ctx->ownStream, &graph);
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(ctx, (int)e, "graph capture (launch)"); }
@@ -329,14 +373,19 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
 
     const size_t fieldBytes = alignUp(sizeof(float) * g.cells * batch, 256);
     const size_t tableBytes = alignUp(spectralTableBytes(g), 256);
-    ctx->arenaBytes = fieldBytes * 8 + tableBytes;
+    {
+        const char* e = getenv("KAMINO_FORK_PARTICLES");
+        ctx->forkParticles = e ? atoi(e) != 0 : true;
+        ctx->velBuffers = ctx->forkParticles ? 3 : 2;
+    }
+    ctx->arenaBytes = fieldBytes * (6 + 2 * ctx->velBuffers) + tableBytes;
     e = cudaMalloc((void**)&ctx->arena, ctx->arenaBytes);
     if (e != cudaSuccess) { int rc = fail(nullptr, (int)e, "cudaMalloc(arena)"); delete ctx; return rc; }
     cudaMemset(ctx->arena, 0, ctx->arenaBytes);
     char* p = ctx->arena;
     auto take = [&p](size_t bytes) { char* r = p; p += bytes; return r; };
-    for (int k = 0; k < 2; ++k) ctx->velPhi[k] = (float*)take(fieldBytes);
-    for (int k = 0; k < 2; ++k) ctx->velTheta[k] = (float*)take(fieldBytes);
+    for (int k = 0; k < ctx->velBuffers; ++k) ctx->velPhi[k] = (float*)take(fieldBytes);
+    for (int k = 0; k < ctx->velBuffers; ++k) ctx->velTheta[k] = (float*)take(fieldBytes);
     for (int k = 0; k < 2; ++k) ctx->density[k] = (float*)take(fieldBytes);
     ctx->pressure = (float*)take(fieldBytes);
     ctx->spectrum = (float2*)take(fieldBytes);
@@ -365,8 +414,13 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         ctx->tables.minusTwoOverH2 = -2.0 / (double)(g.h * g.h);
     }
 
-    bool ok = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) == cudaSuccess
+    int prioLeast = 0, prioGreatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
+    bool ok = cudaStreamCreateWithPriority(&ctx->ownStream, cudaStreamNonBlocking, prioGreatest) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) == cudaSuccess
+        && cudaStreamCreateWithPriority(&ctx->sideStream, cudaStreamNonBlocking, prioLeast) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreate(&ctx->evStart) == cudaSuccess && cudaEventCreate(&ctx->evStop) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->evSnap, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming) == cudaSuccess;
@@ -402,6 +456,9 @@ int kamino_destroy(kamino_ctx* ctx)
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
     if (ctx->evSnap) cudaEventDestroy(ctx->evSnap);
     if (ctx->evCopied) cudaEventDestroy(ctx->evCopied);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->sideStream) cudaStreamDestroy(ctx->sideStream);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->arena) cudaFree(ctx->arena);
@@ -503,7 +560,13 @@ int kamino_particles_device_ptr(kamino_ctx* ctx, int sim, int which, void** devi
 int kamino_advect(kamino_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
-    return timedPhase(ctx, ctx->advectionTime, [&](IndexState& st) { return enqueueAdvect(ctx, st, ctx->stream); });
+    return timedPhase(ctx, ctx->advectionTime, [&](IndexState& st) {
+        if (particlesForked(ctx)) {
+            cudaError_t e = enqueueParticles(ctx, st, ctx->stream);
+            if (e != cudaSuccess) return e;
+        }
+        return enqueueAdvect(ctx, st, ctx->stream);
+    });
 }
 
 int kamino_geometric(kamino_ctx* ctx)
@@ -542,7 +605,7 @@ int kamino_band_advect(kamino_ctx* ctx, int rowBegin, int rowCount)
     AdvectArgs a = advectArgs(ctx, st);
     a.particles = nullptr; a.particlesOut = nullptr;
     KB_TRY(ctx, launchAdvect(g, a, 1, ctx->stream));
-    ctx->velIdx ^= 1; ctx->densityIdx ^= 1;
+    ctx->velIdx = nextVel(ctx, ctx->velIdx); ctx->densityIdx ^= 1;
     return 0;
 }
 
@@ -552,8 +615,8 @@ int kamino_band_geometric(kamino_ctx* ctx, int rowBegin, int rowCount)
     if (int rc = bandRange(ctx, rowBegin, rowCount, 8, &g)) return rc;
     DeviceGuard guard(ctx->device);
     KB_TRY(ctx, launchGeometric(g, ctx->tables, ctx->velPhi[ctx->velIdx], ctx->velTheta[ctx->velIdx],
-                                ctx->velPhi[ctx->velIdx ^ 1], ctx->velTheta[ctx->velIdx ^ 1], 1, ctx->stream));
-    ctx->velIdx ^= 1;
+                                ctx->velPhi[nextVel(ctx, ctx->velIdx)], ctx->velTheta[nextVel(ctx, ctx->velIdx)], 1, ctx->stream));
+    ctx->velIdx = nextVel(ctx, ctx->velIdx);
     return 0;
 }
 
@@ -614,6 +677,7 @@ int kamino_step(kamino_ctx* ctx, int nSteps)
         if (int rc = getGraph(ctx, take, &exec)) return rc;
         KB_TRY(ctx, cudaGraphLaunch(exec, ctx->stream));
         if (take & 1) { ctx->densityIdx ^= 1; ctx->particleIdx ^= 1; }
+        ctx->velIdx = (ctx->velIdx + 2 * take) % ctx->velBuffers;
         remaining -= take;
     }
     return 0;
@@ -675,20 +739,26 @@ int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, floa
     return 0;
 }
 
-int kamino_launches_per_step(const kamino_ctx*) { return kStepKernels; }
+int kamino_launches_per_step(const kamino_ctx* ctx) { return kStepKernels + ((ctx && particlesForked(ctx)) ? 1 : 0); }
 
 int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds)
 {
     if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
     if (nSteps < 1 || !kernelSeconds) return fail(ctx, KAMINO_ERR_INVALID, "nSteps >= 1 and an output array required");
     DeviceGuard guard(ctx->device);
-    std::vector<cudaEvent_t> ev((size_t)nSteps * (kStepKernels + 1));
+    const bool forked = particlesForked(ctx);
+    const int nK = kStepKernels + (forked ? 1 : 0);          // slot 5 = the particle kernel
+    std::vector<cudaEvent_t> ev((size_t)nSteps * (nK + 1));
     for (auto& e : ev) KB_TRY(ctx, cudaEventCreate(&e));
     IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
     cudaError_t err = cudaSuccess;
     for (int s = 0; s < nSteps && err == cudaSuccess; ++s) {
-        cudaEvent_t* e = &ev[(size_t)s * (kStepKernels + 1)];
+        cudaEvent_t* e = &ev[(size_t)s * (nK + 1)];
         err = cudaEventRecord(e[0], ctx->stream);
+        if (forked && err == cudaSuccess) {                   // launched first: it reads the pre-advection velocity
+            err = enqueueParticles(ctx, st, ctx->stream);
+            if (err == cudaSuccess) err = cudaEventRecord(e[nK], ctx->stream);
+        }
         for (int k = 0; k < kStepKernels && err == cudaSuccess; ++k) {
             err = enqueueStepKernel(ctx, st, k, ctx->stream);
             if (err == cudaSuccess) err = cudaEventRecord(e[k + 1], ctx->stream);
@@ -696,19 +766,21 @@ int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds)
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
     ctx->velIdx = st.vel; ctx->densityIdx = st.density; ctx->particleIdx = st.particle;
-    double total[kStepKernels] = {};
+    std::vector<double> total(nK, 0.0);
     for (int s = 0; s < nSteps && err == cudaSuccess; ++s) {
-        cudaEvent_t* e = &ev[(size_t)s * (kStepKernels + 1)];
-        for (int k = 0; k < kStepKernels; ++k) {
+        cudaEvent_t* e = &ev[(size_t)s * (nK + 1)];
+        for (int k = 0; k < nK && err == cudaSuccess; ++k) {
             float ms = 0.f;
-            err = cudaEventElapsedTime(&ms, e[k], e[k + 1]);
-            if (err != cudaSuccess) break;
+            // event order in the stream: e[0], (e[nK] after the particles,) e[1] .. e[5]
+            cudaEvent_t from = (k == 0) ? (forked ? e[nK] : e[0]) : (k == kStepKernels ? e[0] : e[k]);
+            cudaEvent_t to = (k == kStepKernels) ? e[nK] : e[k + 1];
+            err = cudaEventElapsedTime(&ms, from, to);
             total[k] += ms * 1e-3;
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
     if (err != cudaSuccess) return fail(ctx, (int)err, "kamino_profile_steps");
-    for (int k = 0; k < kStepKernels; ++k) kernelSeconds[k] = (float)total[k];
+    for (int k = 0; k < nK; ++k) kernelSeconds[k] = (float)total[k];
     return 0;
 }
 

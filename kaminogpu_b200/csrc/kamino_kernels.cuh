@@ -41,6 +41,8 @@ struct AdvectArgs {
 };
 
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
+// the tracer particles alone (a.particles / a.particlesOut / a.velPhi / a.velTheta / a.consts); a plain launch
+cudaError_t launchAdvectParticles(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
 
 struct SamplerConsts;
 cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const float* phiRaw, const float* thetaRaw,

@@ -25,8 +25,10 @@ def main():
     w = sys.argv[1] if len(sys.argv) > 1 else "c2"
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     nT, pd = W[w]
-    names = {31: "all", 1: "advect", 2: "geometric", 4: "divergence_fft", 8: "tridiagonal", 16: "inverse_fft_gradient",
-             3: "advect+geometric", 28: "projection", 30: "all but advect"}
+    # bit 5 = the particle kernel (its own kernel on a parallel graph branch when the context holds particles)
+    names = {63: "all", 31: "all but particles", 1: "advect (cells)", 32: "particles", 33: "advect + particles",
+             2: "geometric", 4: "divergence_fft", 8: "tridiagonal", 16: "inverse_fft_gradient",
+             28: "projection", 30: "geometric + projection", 62: "all but advect (cells)"}
     for mask, name in names.items():
         env = dict(os.environ, KAMINO_DEBUG_STEP_MASK=str(mask))
         out = subprocess.run([sys.executable, "-c", CHILD, str(nT), str(pd), str(K)], env=env, capture_output=True, text=True)
