@@ -106,8 +106,8 @@ int kamino_upload_particles_async(kamino_ctx* ctx, int sim, const float* pinnedH
 /* KaminoQuantity::getGPUThisStep / getGPUNextStep / get*PitchInElements
  * (include/KaminoQuantity.cuh:60-66): raw device pointer of the current this/next buffer
  * (which = 0 / 1) and its pitch in elements. The roles move after every phase as the
- * reference's swaps do (the velocity rotates through three buffers instead of two, so
- * re-query the pointers after a phase rather than swapping a cached pair). */
+ * reference's swaps do (re-query the pointers after a phase rather than swapping a cached
+ * pair: the forked-particles mode rotates the velocity through three buffers). */
 int kamino_field_device_ptr(kamino_ctx* ctx, int field, int sim, int which,
                             void** devicePtr, size_t* pitchInElements);
 /* KaminoParticles::coordGPUThisStep / coordGPUNextStep (include/KaminoParticles.cuh:18-19). */
@@ -171,9 +171,8 @@ int kamino_run_frames(kamino_ctx* ctx, int nFrames, int stepsPerFrame,
 int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, float* projection, int reset);
 
 /* Number of kernel launches one kamino_step(ctx, 1) performs (for bench.py's gpu_launches):
- * 5, or 6 when the context holds particles and they run as their own kernel on a parallel
- * branch of the step graph (the default; KAMINO_FORK_PARTICLES=0 fuses them into the
- * advection launch). */
+ * 5 (the particles are part of the advection launch), or 6 with KAMINO_FORK_PARTICLES=1
+ * (experimental: particles as their own kernel on a parallel branch of the step graph). */
 int kamino_launches_per_step(const kamino_ctx* ctx);
 
 /* Run nSteps steps with every kernel launched individually and bracketed by CUDA events on

@@ -138,8 +138,18 @@ template <int SIGN> KB_HD void dft16(float2* v)
         }
 }
 
-// Twiddle table: tw[p] = exp(-2*pi*i*p/N), p = 0..N-1 (forward sign); conjugated for SIGN > 0.
-// (`tw` may point to global or to shared memory, so this is a plain load)
+// Twiddle tables. Only the radix-16 passes after the first pass need inter-pass twiddles: the
+// pass that starts from Ns already-transformed points multiplies element m (1..15) of butterfly
+// k = tb mod Ns by exp(-2*pi*i * k*m / (16*Ns)). One table per such pass, laid out [m-1][k]
+// (k fastest): the threads of a warp hold consecutive k for the same m, so a warp reads
+// consecutive float2 (conflict-free from shared memory; with the single N-entry table indexed
+// k*m*N/(16*Ns) the 16 distinct k of the second pass all fell on the same bank: 69 % of the
+// shared-memory wavefronts of the r01f inverse FFT were bank-conflict replays). The tables of
+// the successive passes are packed back to back: 15*Ns entries each, N - firstRadix in total.
+// Forward sign stored; conjugated for SIGN > 0. (`tw` may point to global or shared memory.)
+KB_HD int firstRadix(int log2N) { return (log2N & 3) ? (1 << (log2N & 3)) : 16; }
+KB_HD int twiddleTableSize(int N, int log2N) { return N - firstRadix(log2N); }
+
 template <int SIGN> KB_HD float2 twiddleAt(const float2* tw, int p)
 {
     float2 w = tw[p];
@@ -150,21 +160,15 @@ template <int SIGN> KB_HD float2 twiddleAt(const float2* tw, int p)
 // One Stockham pass of radix R over the 16 values of thread t (T = N/16 threads per transform).
 //   v[e] holds in[t + e*T] on entry; the function twiddles, transforms and scatters to `out`
 //   (padded shared memory, or any array indexed through pad()).
-//   Ns = product of the radices of the previous passes.
+//   Ns = product of the radices of the previous passes; twPass = this pass's [m-1][k] table
+//   (unused by the first pass, Ns == 1, the only one that may have R < 16).
 template <int SIGN, int R>
-KB_HD void passCompute(float2* v, int t, int T, int N, int Ns, const float2* tw)
+KB_HD void passCompute(float2* v, int t, int T, int N, int Ns, const float2* twPass)
 {
-    constexpr int Q = 16 / R;          // butterflies per thread
-    // butterfly q uses elements e = q + m*Q (m = 0..R-1); its index is tb = t + q*T
-    if (Ns > 1) {
-        const int twStride = N / (Ns * R);
+    if (R == 16 && Ns > 1) {
+        const int k = t & (Ns - 1);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int k = (t + q * T) & (Ns - 1);
-#pragma unroll
-            for (int m = 1; m < R; ++m)
-                v[q + m * Q] = cmul(v[q + m * Q], twiddleAt<SIGN>(tw, k * m * twStride));
-        }
+        for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], twiddleAt<SIGN>(twPass, (m - 1) * Ns + k));
     }
     if (R == 16) dft16<SIGN>(v);
     else if (R == 8) { dft8<SIGN, 2>(v); dft8<SIGN, 2>(v + 1); }

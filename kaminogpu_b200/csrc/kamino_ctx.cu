@@ -1,15 +1,15 @@
 // Context, memory layout, step graphs and the C ABI of kamino_b200 (include/kamino_b200.h).
 //
 // HBM layout (one arena per context, every sub-buffer 256-byte aligned, batch-major):
-//   velPhi[3], velTheta[3], density[2]   batch x nTheta x nPhi fp32 each (u_theta uses
-//                                        nTheta-1 rows of its slot); density is double-buffered,
-//                                        the velocity rotates through three buffers (see below)
+//   velPhi[2], velTheta[2], density[2]   batch x nTheta x nPhi fp32 each (u_theta uses
+//                                        nTheta-1 rows of its slot), double-buffered (a third
+//                                        velocity buffer in the forked-particles mode, see below)
 //   pressure                             batch x nTheta x nPhi fp32
 //   spectrum                             batch x nTheta x nPhi/2 float2 (half spectrum)
 //   particles[2]                         batch x numParticles float2, double-buffered
 //   tables                               twiddles + per-row constants + the LU factors of every
 //                                        wavenumber's theta system (10 B per cell, read-only)
-// = 44 B/cell of state + 10 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
+// = 36 B/cell of state + 10 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
 // SURVEY.md appendix B).
 #include <cstdio>
 #include <cstdlib>
@@ -49,13 +49,16 @@ struct kamino_ctx {
 
     int velIdx = 0, densityIdx = 0, particleIdx = 0;   // which buffer is "this step"
     // Velocity buffers in rotation. advect writes next(v), geometric writes next(next(v)), the
-    // projection corrects that buffer in place. With three buffers the pre-advection velocity of
-    // step n stays untouched until advect of step n+1, so the tracer particles of step n (which read
+    // projection corrects that buffer in place; two buffers by default (a ping-pong, as in the
+    // reference). KAMINO_FORK_PARTICLES=1 selects three buffers: the pre-advection velocity of step
+    // n then stays untouched until advect of step n+1, so the tracer particles of step n (which read
     // only that velocity, kernel/KaminoCore.cu:376-381) run as their own kernel on a parallel
-    // branch of the step graph, in the shadow of the latency-bound geometric and projection
-    // kernels. KAMINO_FORK_PARTICLES=0 restores two buffers and the fused advection launch.
-    int velBuffers = 3;
-    bool forkParticles = true;
+    // branch of the step graph. Measured (r01i, C2): 63.9 us/step forked against 54.5 us fused --
+    // inside the fused launch the particle blocks fill the tail waves of the tile blocks at a
+    // marginal cost of 8 us, while the separate kernel needs 20 us and competes with the velocity
+    // chain for SM slots -- so the fused launch stays the default.
+    int velBuffers = 2;
+    bool forkParticles = false;
 
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (parity, steps) -> exec
 
@@ -375,7 +378,7 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
     const size_t tableBytes = alignUp(spectralTableBytes(g), 256);
     {
         const char* e = getenv("KAMINO_FORK_PARTICLES");
-        ctx->forkParticles = e ? atoi(e) != 0 : true;
+        ctx->forkParticles = e ? atoi(e) != 0 : false;
         ctx->velBuffers = ctx->forkParticles ? 3 : 2;
     }
     ctx->arenaBytes = fieldBytes * (6 + 2 * ctx->velBuffers) + tableBytes;

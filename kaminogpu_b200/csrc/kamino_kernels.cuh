@@ -52,7 +52,7 @@ cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const fl
 // Per-context read-only per-row tables (built once by launchBuildTables with the same device
 // functions the reference's kernels call per thread, so every entry is bit-identical).
 struct SpectralTables {
-    float2* twiddle;      // nPhi entries: exp(-2 pi i k / nPhi)
+    float2* twiddle;      // packed per-pass FFT twiddle tables (fft_core.cuh), < nPhi entries
     float* divFactor;     // nTheta: invGridSine / gridLen        (kernel/KaminoCore.cu:625,628)
     float* sinNorth;      // nTheta: sinf(theta_j - h/2)          (:626)
     float* sinSouth;      // nTheta: sinf(theta_j + h/2)          (:627)

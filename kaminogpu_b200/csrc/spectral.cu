@@ -50,11 +50,13 @@ __device__ __forceinline__ void fftFromRegisters(float2* v, float2* buf, int t, 
     }
     if (twReady) tma::mbarWait(twReady, 0);
     __syncthreads();
+    const float2* twPass = tw;                 // packed per-pass tables, fft_core.cuh
     while (Ns < N) {
         passGather(v, buf, t, T);
         __syncthreads();                       // everyone has read before anyone overwrites
-        passCompute<SIGN, 16>(v, t, T, N, Ns, tw);
+        passCompute<SIGN, 16>(v, t, T, N, Ns, twPass);
         passScatter<16>(v, buf, t, T, Ns);
+        twPass += 15 * Ns;
         Ns <<= 4;
         __syncthreads();
     }
@@ -65,9 +67,13 @@ __device__ __forceinline__ void fftFromRegisters(float2* v, float2* buf, int t, 
 __global__ void buildTablesKernel(GridParams g, SpectralTables t)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < g.nPhi) {
+    if (k < fft::twiddleTableSize(g.nPhi, g.log2NPhi)) {
+        // entry k of the packed per-pass tables: pass with Ns points done, element m, butterfly kk
+        int Ns = fft::firstRadix(g.log2NPhi), rel = k;
+        while (rel >= 15 * Ns) { rel -= 15 * Ns; Ns <<= 4; }
+        const int m = rel / Ns + 1, kk = rel - (m - 1) * Ns;
         double s, c;
-        sincospi(-2.0 * (double)k / (double)g.nPhi, &s, &c);
+        sincospi(-2.0 * (double)(kk * m) / (double)(16 * Ns), &s, &c);
         t.twiddle[k] = make_float2((float)c, (float)s);
     }
     if (k < g.nTheta) {
@@ -121,14 +127,14 @@ __device__ __forceinline__ float divergenceAt(const GridParams& g, const Spectra
 // the second pass. Returns the barrier to wait on (NULL when the table stays in global memory).
 template <bool STAGE>
 __device__ __forceinline__ uint64_t* stageTwiddles(const float2* __restrict__ twGlobal, float2* twShared,
-                                                   uint64_t* bar, int N)
+                                                   uint64_t* bar, int twEntries)
 {
     if (!STAGE) return nullptr;
     if (threadIdx.x == 0) { tma::mbarInit(bar, 1); tma::fenceBarrierInit(); }
     __syncthreads();
     if (threadIdx.x == 0) {
-        tma::mbarExpectTx(bar, (uint32_t)(N * sizeof(float2)));
-        tma::bulkLoad(twShared, twGlobal, (uint32_t)(N * sizeof(float2)), bar);
+        tma::mbarExpectTx(bar, (uint32_t)(twEntries * sizeof(float2)));
+        tma::bulkLoad(twShared, twGlobal, (uint32_t)(twEntries * sizeof(float2)), bar);
     }
     return bar;
 }
@@ -156,7 +162,7 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
     const float* velTheta = velThetaAll + (size_t)sim * g.cells;
     float2* spectrum = spectrumAll + (size_t)sim * (g.cells >> 1);
 
-    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, N);
+    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, g.log2NPhi));
     const float2* tw = STAGE ? twShared : t.twiddle;
     pdlWait();                                   // the velocity comes from the previous kernel
 
@@ -245,7 +251,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
     const float2* rowU = spectrum + (size_t)j * half;
     const float2* rowS = spectrum + (size_t)(hasSouth ? j + 1 : j) * half;     // !hasSouth: Y = 0
 
-    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, N);
+    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, g.log2NPhi));
     const float2* tw = STAGE ? twShared : t.twiddle;
     pdlWait();                                   // the spectrum comes from the previous kernel
 

@@ -19,18 +19,20 @@ static void runFFT(std::vector<float2>& data, int N, int log2N, const std::vecto
     int Ns = 1;
     const int lead = log2N & 3;
     bool first = true;
+    const float2* twPass = tw.data();
     while (Ns < N) {
         int R = 16;
         if (first && lead) R = 1 << lead;
         for (int t = 0; t < T; ++t) {
             float2 v[16];
             passGather(v, a.data(), t, T);
-            if (R == 16) { passCompute<SIGN, 16>(v, t, T, N, Ns, tw.data()); passScatter<16>(v, b.data(), t, T, Ns); }
-            else if (R == 8) { passCompute<SIGN, 8>(v, t, T, N, Ns, tw.data()); passScatter<8>(v, b.data(), t, T, Ns); }
-            else if (R == 4) { passCompute<SIGN, 4>(v, t, T, N, Ns, tw.data()); passScatter<4>(v, b.data(), t, T, Ns); }
-            else { passCompute<SIGN, 2>(v, t, T, N, Ns, tw.data()); passScatter<2>(v, b.data(), t, T, Ns); }
+            if (R == 16) { passCompute<SIGN, 16>(v, t, T, N, Ns, twPass); passScatter<16>(v, b.data(), t, T, Ns); }
+            else if (R == 8) { passCompute<SIGN, 8>(v, t, T, N, Ns, twPass); passScatter<8>(v, b.data(), t, T, Ns); }
+            else if (R == 4) { passCompute<SIGN, 4>(v, t, T, N, Ns, twPass); passScatter<4>(v, b.data(), t, T, Ns); }
+            else { passCompute<SIGN, 2>(v, t, T, N, Ns, twPass); passScatter<2>(v, b.data(), t, T, Ns); }
         }
         a.swap(b);
+        if (!first) twPass += 15 * Ns;
         Ns *= R;
         first = false;
     }
@@ -42,10 +44,19 @@ int main()
     int failures = 0;
     for (int log2N = 4; log2N <= 14; ++log2N) {
         const int N = 1 << log2N;
+        // packed per-pass tables [m-1][k] (fft_core.cuh), built as buildTablesKernel does
         std::vector<float2> tw(N);
-        for (int p = 0; p < N; ++p) {
-            const double ang = -2.0 * M_PI * p / N;
-            tw[p] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        {
+            int off = 0;
+            for (int Ns = firstRadix(log2N); Ns < N; Ns <<= 4) {
+                for (int m = 1; m < 16; ++m)
+                    for (int k = 0; k < Ns; ++k) {
+                        const double ang = -2.0 * M_PI * (double)(k * m) / (double)(16 * Ns);
+                        tw[off + (m - 1) * Ns + k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+                    }
+                off += 15 * Ns;
+            }
+            if (off != twiddleTableSize(N, log2N)) { std::printf("table size mismatch\n"); return 1; }
         }
         for (int sign = -1; sign <= 1; sign += 2) {
             std::vector<float2> x(N);
