@@ -71,6 +71,36 @@ __device__ __forceinline__ float backtrace(const SamplerRegs& g, const SamplerCo
 // Tried and rejected (r01g/r01h A/B): advancing the three backtraces of a cell stage by stage so
 // that six samples are in flight per round -- 80-100 registers, 10 % slower than this form.
 
+// backtrace() of an interior block without a branch: see sampleIssueFast. `bad` comes back true for
+// the lanes whose result must be discarded.
+template <int KIND>
+__device__ __forceinline__ float backtraceFast(const SamplerRegs& g, float cofTheta, int i, int j, float cofPhi,
+                                               unsigned tilePhi, unsigned tileTheta, unsigned tileSrc, bool& bad)
+{
+    const float offPhi = (KIND == kVPhi) ? -0.5f : 0.0f;
+    const float offTheta = (KIND == kVTheta) ? 1.0f : 0.5f;
+    const float gPhi = __fmul_rn(__fadd_rn((float)i, offPhi), g.h);
+    const float gTheta = __fmul_rn(__fadd_rn((float)j, offTheta), g.h);
+    bad = false;
+    PendingSample pu = sampleIssueFast<kVPhi>(g, gPhi, gTheta, tilePhi, bad);
+    PendingSample pv = sampleIssueFast<kVTheta>(g, gPhi, gTheta, tileTheta, bad);
+    const float guPhi = sampleFinish(pu);
+    const float guTheta = sampleFinish(pv);
+    const float deltaPhi = __fmul_rn(guPhi, cofPhi);
+    const float deltaTheta = __fmul_rn(guTheta, cofTheta);
+    const float midPhi = __fmaf_rn(-0.5f, deltaPhi, gPhi);
+    const float midTheta = __fmaf_rn(-0.5f, deltaTheta, gTheta);
+    pu = sampleIssueFast<kVPhi>(g, midPhi, midTheta, tilePhi, bad);
+    pv = sampleIssueFast<kVTheta>(g, midPhi, midTheta, tileTheta, bad);
+    const float muPhi = sampleFinish(pu);
+    const float muTheta = sampleFinish(pv);
+    const float averuPhi = __fmul_rn(0.5f, __fadd_rn(muPhi, guPhi));
+    const float averuTheta = __fmul_rn(0.5f, __fadd_rn(muTheta, guTheta));
+    const float pPhi = __fmaf_rn(-averuPhi, cofPhi, gPhi);
+    const float pTheta = __fmaf_rn(-averuTheta, cofTheta, gTheta);
+    return sampleFinish(sampleIssueFast<KIND>(g, pPhi, pTheta, tileSrc, bad));
+}
+
 // kernel/KaminoCore.cu:321-342, in two halves so that a thread can have the gathers of several
 // particles in flight: the two velocity samples are issued, then finished and applied.
 struct PendingParticle { PendingSample u, v; };
@@ -173,22 +203,27 @@ advectKernel(GridParams g, AdvectArgs a)
         // blocks whose tile lies inside rows [2, nTheta-4] and columns [2, N-2]: see sampleIssueTiled
         const bool safe = tr.tileRow0 >= 2 && tr.tileRow0 + (kTileH - 1) <= sr.nTheta - 4
                        && tr.tileCol0 >= 2 && tr.tileCol0 + (kTileW - 1) <= sr.N - 2;
+        const float cofTheta = __ldg(a.cofPhiTheta + j);
+        // interior blocks: the three backtraces without a branch; a lane whose samples left the tile
+        // (or a block that is not interior) redoes the backtrace below with the branching samplers
+        bool redoU = true, redoV = true, redoRho = true;
         if (safe) {
-            a.velPhiOut[cell] = backtrace<kVPhi, true>(tr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred,
-                                                       tPhi, tTheta, tPhi);
-            a.velThetaOut[cell] = backtrace<kVTheta, true>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
-                                                           __ldg(a.cofPhiTheta + j), tPhi, tTheta, tTheta);
-            a.densityOut[cell] = backtrace<kCentered, true>(tr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j,
-                                                            cofCentred, tPhi, tTheta, tRho);
-        } else {
+            const float u = backtraceFast<kVPhi>(tr, g.cofTheta, i, j, cofCentred, tPhi, tTheta, tPhi, redoU);
+            const float v = backtraceFast<kVTheta>(tr, g.cofTheta, i, j, cofTheta, tPhi, tTheta, tTheta, redoV);
+            const float rho = backtraceFast<kCentered>(tr, g.cofTheta, i, j, cofCentred, tPhi, tTheta, tRho, redoRho);
+            if (!redoU) a.velPhiOut[cell] = u;
+            if (!redoV) a.velThetaOut[cell] = v;           // interior blocks never hold row nTheta-1
+            if (!redoRho) a.densityOut[cell] = rho;
+        }
+        if (redoU)
             a.velPhiOut[cell] = backtrace<kVPhi, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, velPhi, i, j, cofCentred,
                                                         tPhi, tTheta, tPhi);
-            if (j < g.nTheta - 1)
-                a.velThetaOut[cell] = backtrace<kVTheta, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
-                                                                __ldg(a.cofPhiTheta + j), tPhi, tTheta, tTheta);
+        if (redoV && j < g.nTheta - 1)
+            a.velThetaOut[cell] = backtrace<kVTheta, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, velTheta, i, j,
+                                                            cofTheta, tPhi, tTheta, tTheta);
+        if (redoRho)
             a.densityOut[cell] = backtrace<kCentered, false>(tr, a.consts, g.cofTheta, velPhi, velTheta, density, i, j,
                                                              cofCentred, tPhi, tTheta, tRho);
-        }
         return;
     }
     long k;

@@ -300,6 +300,35 @@ __device__ __forceinline__ PendingSample sampleIssueTiled(const SamplerRegs& g, 
     return p;
 }
 
+// Branch-free form of the SAFE tile sample (interior blocks of the advection kernel): the fast-path
+// arithmetic is executed unconditionally, the tile address of a lane that fails the tile test is
+// clamped to a valid one, and the failure is recorded in the sticky flag `bad`. The caller discards
+// everything a flagged lane computed and redoes that backtrace with sampleIssueTiled<KIND, false>,
+// so the values of unflagged lanes are exactly those of the branching form; what goes away is
+// the divergence bookkeeping around every sample (two branches, BSSY, BSYNC) and, with the call
+// to the out-of-line general path gone from the hot loop, the register spills around it.
+template <int KIND>
+__device__ __forceinline__ PendingSample sampleIssueFast(const SamplerRegs& g, float phiRaw, float thetaRaw,
+                                                         unsigned tile, bool& bad)
+{
+    const float phi = (KIND == kVPhi) ? __fadd_rn(phiRaw, g.halfH) : phiRaw;
+    const float theta = (KIND == kVTheta) ? __fsub_rn(thetaRaw, g.h) : __fsub_rn(thetaRaw, g.halfH);
+    const float normedPhi = __fmul_rn(phi, g.invH);
+    const float normedTheta = __fmul_rn(theta, g.invH);
+    const int phiIndex = (int)floorf(normedPhi);
+    const int thetaIndex = (int)floorf(normedTheta);
+    const int tr = thetaIndex - g.tileRow0;
+    const int tc = phiIndex - g.tileCol0;
+    bad = bad || (unsigned)tr >= (unsigned)(kTileH - 1) || (unsigned)tc >= (unsigned)(kTileW - 1);
+    // valid lanes: tr * kTileW + tc <= (kTileH - 2) * kTileW + kTileW - 2, never altered by the clamp
+    const unsigned cellIndex = min((unsigned)(tr * kTileW + tc), (unsigned)((kTileH - 2) * kTileW + kTileW - 2));
+    PendingSample p;
+    p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
+    p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
+    loadTileCell(tile + 4u * cellIndex, p);
+    return p;
+}
+
 template <int KIND>
 __device__ __forceinline__ PendingSample sampleIssue(const SamplerRegs& g, const SamplerConsts* __restrict__ consts,
                                                      const float* __restrict__ field, float phiRaw, float thetaRaw)
