@@ -324,8 +324,9 @@ void fillSamplerConsts(const GridParams& g, void* hostBlock64)
 
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
 {
-    // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget), default 5
-    static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 5; }();
+    // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget). r01k A/B with the
+    // branch-free interior path (C3 advect): 4 -> 217.6 us, 5 -> 209.1 us, 6 -> 198.6 us; equal at C2
+    static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 6; }();
     a.tileBlocks = (g.nPhi / 32) * (g.rowCount / kTileRows);      // rowBegin, rowCount: multiples of kTileRows
     int blocksParticles = (a.particles && g.numParticles > 0)
         ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
@@ -357,8 +358,9 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
     switch (variant) {
     case 3: return launchChained(advectKernel<3>, grid, dim3(kAdvectThreads), 0, stream, g, a);
     case 4: return launchChained(advectKernel<4>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    case 6: return launchChained(advectKernel<6>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    default: return launchChained(advectKernel<5>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    case 5: return launchChained(advectKernel<5>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    case 7: return launchChained(advectKernel<7>, grid, dim3(kAdvectThreads), 0, stream, g, a);
+    default: return launchChained(advectKernel<6>, grid, dim3(kAdvectThreads), 0, stream, g, a);
     }
 }
 

@@ -1,4 +1,5 @@
 #include "KaminoSolver.h"
+#include "ImageIO.h"
 
 #include <cstdlib>
 
@@ -70,11 +71,26 @@ void KaminoSolver::initialize_velocity()
     velTheta->copyToGPU();
 }
 
-// kernel/KaminoSolver.cu:243-277. Only the no-image path belongs to the solver path.
+// kernel/KaminoSolver.cu:243-277: density = mean of the B, G, R channels of the image, mirrored
+// and resized to nPhi x nTheta (imread / flip / resize without OpenCV: ImageIO.h).
 void KaminoSolver::initDensityfromPic(std::string path)
 {
     if (path == "") return;
-    std::cerr << "No density image provided." << std::endl;   // what the reference prints when imread fails
+    ImageBGR imageIn;
+    if (!readImageBGR(path, imageIn)) {
+        std::cerr << "No density image provided." << std::endl;
+        return;
+    }
+    const ImageBGR resized = resizeLinear(flipHorizontal(imageIn), (int)nPhi, (int)nTheta);
+    for (size_t i = 0; i < nPhi; ++i)
+        for (size_t j = 0; j < nTheta; ++j) {
+            const unsigned char* p = resized.pixel((int)j, (int)i);
+            const fReal B = (fReal)(p[0] / 255.0);
+            const fReal G = (fReal)(p[1] / 255.0);
+            const fReal R = (fReal)(p[2] / 255.0);
+            density->setCPUValueAt(i, j, (fReal)((B + G + R) / 3.0));
+        }
+    density->copyToGPU();
 }
 
 // kernel/KaminoSolver.cu:279-282
