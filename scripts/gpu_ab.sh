@@ -5,7 +5,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 for v in $VARIANTS; do
   for w in $WL; do
-    steps=1000; [ $w = c3 ] && steps=100
+    steps=1000; [ $w = c3 ] && steps=100; [ $w = c4 ] && steps=100
     env $(echo $v | tr "," " ") timeout 600 python bench.py --workload $w --steps $steps --warmup 10 --no-cpu-baseline > $OUT/bench_${w}_$v.json 2> $OUT/bench_${w}_$v.err
     python - <<PY
 import json

@@ -527,6 +527,81 @@ def test_cli_runs_config_file(K, tmp_path):
             assert version == 5 and points == npts
 
 
+def test_cli_image_driven_initialisation(K, tmp_path):
+    """densityImage / colorImage tokens of configKamino.txt (kernel/main.cu:40-45): the density and the
+    particle colours come from the mirrored, resized image (kernel/KaminoSolver.cu:243-277,
+    kernel/KaminoParticles.cu:64-72). Frame 0 is written before any step, so its density attribute must
+    equal the committed cv2-derived golden bit for bit."""
+    import gzip
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    image = os.path.join(root, "tests", "golden", "images", "smooth.png")
+    cfg = tmp_path / "configKamino.txt"
+    (tmp_path / "out").mkdir()
+    cfg.write_text("5.0 32 1.0 0.005 0.041666668 1 0.0 1 1 1 1 %s/out/f %s/out/p %s null %s\n" % (tmp_path, tmp_path, image, image))
+    out = subprocess.run([os.path.join(root, "kaminogpu_b200", "kamino"), str(cfg)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "No density image provided" not in out.stderr and "No particle color image provided" not in out.stderr
+    want = np.load(os.path.join(root, "tests", "golden", "image_init.npz"))["smooth.png.32x64.density"]
+
+    def read_bgeo(path):
+        """-> {attribute name: (points x count) float32}, points (positions are implicit, 4 floats)."""
+        import struct
+        raw = gzip.open(path).read()
+        assert raw[:5] == b"BgeoV"
+        version, points, _, _, _, nattr, _, _, _ = struct.unpack(">9i", raw[5:41])
+        pos, attrs = 41, []
+        for _ in range(nattr):
+            (ln,) = struct.unpack(">H", raw[pos:pos + 2]); pos += 2
+            name = raw[pos:pos + ln].decode(); pos += ln
+            count, _type = struct.unpack(">HI", raw[pos:pos + 6]); pos += 6 + 4 * count
+            attrs.append((name, count))
+        per = 4 + sum(c for _, c in attrs)
+        data = np.frombuffer(raw[pos:pos + 4 * per * points], dtype=">f4").reshape(points, per).astype(np.float32)
+        out, col = {}, 4
+        for name, count in attrs:
+            out[name] = data[:, col:col + count]; col += count
+        return out
+
+    grid = read_bgeo(str(tmp_path / "out" / "f0.bgeo"))
+    # the writer walks the grid theta-major or phi-major; either way the multiset of values is the golden's
+    got = np.sort(grid["density"].ravel())
+    assert np.array_equal(got.view(np.uint32), np.sort(want.ravel()).view(np.uint32))
+    parts = read_bgeo(str(tmp_path / "out" / "p0.bgeo"))
+    assert parts["color"].shape == (2048, 3) and parts["color"].max() > 0.0      # particles are not black
+
+
+def test_forked_particles_mode_is_bit_identical(K, tmp_path):
+    """KAMINO_FORK_PARTICLES=1 (particles as their own kernel on a parallel graph branch, three
+    rotating velocity buffers) must produce the bits of the default fused launch."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import oracle_api as oa\n"
+        "from kaminogpu_b200.solver import KaminoSolver\n"
+        "g = oa.golden('t32'); nT = 32\n"
+        "s = KaminoSolver(64, nT, float(g['meta.radius']), float(g['meta.dt']))\n"
+        "s.density.cpuBuffer[:] = g['init.density'].reshape(nT, 64); s.density.copyToGPU()\n"
+        "s.initParticlesfromPic('', 0, coords=g['init.particles'])\n"
+        "s.stepForward(nSteps=13); s.advection(); s.geometric(); s.projection(); s.stepForward(nSteps=2); s.sync()\n"
+        "np.savez(sys.argv[1], u=s.velPhi.copyBackToCPU(), v=s.velTheta.copyBackToCPU(), r=s.density.copyBackToCPU(), p=s.particles.copyBack2CPU())\n"
+    ) % (root, os.path.join(root, "tests"))
+    outs = []
+    for fork in ("0", "1"):
+        path = str(tmp_path / ("state%s.npz" % fork))
+        env = dict(os.environ, KAMINO_FORK_PARTICLES=fork)
+        run = subprocess.run([sys.executable, "-c", script, path], env=env, capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0, run.stderr[-2000:]
+        outs.append(np.load(path))
+    for name in ("u", "v", "r", "p"):
+        assert np.array_equal(outs[0][name].view(np.uint32), outs[1][name].view(np.uint32)), name
+
+
 # ---- theta-band decomposition (SURVEY.md 8e): virtual ranks on one GPU ----------------------------
 
 @pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
