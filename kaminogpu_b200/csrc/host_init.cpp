@@ -45,10 +45,12 @@ float valueNoise(float x, float y)
 float fbm(float x, float y)
 {
     const float resX = 0.15f, resY = 0.5f, persistence = 0.5f;
+    // freq = (fReal)pow(2.0, octave) and amp = (fReal)pow(persistence, octave) are exact powers of two
+    static const float freqs[4] = {1.0f, 2.0f, 4.0f, 8.0f}, amps[4] = {1.0f, 0.5f, 0.25f, 0.125f};
     float total = 0.0f;
     for (int octave = 0; octave < 4; ++octave) {
-        const float freq = (float)std::pow(2.0, (double)octave);
-        const float amp = (float)std::pow((double)persistence, (double)octave);
+        const float freq = freqs[octave];
+        const float amp = amps[octave];
         total += amp * valueNoise(x * freq / resX, y * freq / resY);
     }
     const float norm = 1 - persistence;
@@ -66,7 +68,10 @@ extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi
     const float scale = radius * h;
 
     // u_phi: theta-difference of the noise, averaged over the two phi sides of the face
-    // (KaminoInitializer.cu:11-55; the i = 0 column wraps to 2*pi - h/2)
+    // (KaminoInitializer.cu:11-55; the i = 0 column wraps to 2*pi - h/2). Every cell is a pure
+    // function of its position, so the rows are spread over the host cores (the reference's serial
+    // double loop takes minutes at 8192 x 16384; the values do not depend on the schedule).
+#pragma omp parallel for schedule(dynamic, 8)
     for (int j = 0; j < nTheta; ++j) {
         const float yUp = (float)(j + 1) * h, yLo = (float)j * h;
         for (int i = 0; i < nPhi; ++i) {
@@ -79,6 +84,7 @@ extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi
     }
     // u_theta: minus the phi-difference; the reference's lower-left sample reuses the upper
     // row (KaminoInitializer.cu:69), which is kept
+#pragma omp parallel for schedule(dynamic, 8)
     for (int j = 1; j < nTheta; ++j) {
         const float yUp = (float)j * h + h / 2, yLo = (float)j * h - h / 2;
         for (int i = 0; i < nPhi; ++i) {

@@ -402,12 +402,6 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
         ctx->tables.gradPhiDenom = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.triA = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.triC = (float*)sub(sizeof(float) * nTheta);
-        ctx->tables.thA = (float*)sub(sizeof(float) * nTheta);
-        ctx->tables.thC = (float*)sub(sizeof(float) * nTheta);
-        {
-            const char* e = getenv("KAMINO_TRI_COMPACT");
-            ctx->tables.compactSolve = e ? (atoi(e) != 0) : 1;
-        }
         ctx->tables.sinSq = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.geoG = (float*)sub(sizeof(float) * nTheta);
         ctx->tables.cofPhiCentred = (float*)sub(sizeof(float) * nTheta);

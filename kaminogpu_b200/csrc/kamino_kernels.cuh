@@ -73,14 +73,6 @@ struct SpectralTables {
     float* thH;           // h_i = c_i / b'_i
     float* thDelta;       // delta_i = prod_{i..chunk end} (-h)
     float* thBetaEnd;     // beta at the last row of every chunk, [slot group][chunk][w]
-    // Compact mode (default; KAMINO_TRI_COMPACT=0 reads thL / thH instead): the multipliers are rebuilt
-    // in the kernel as l_i = a_i * (1/b'_{i-1}) and h_i = c_i * (1/b'_i) from the per-row off-diagonals
-    // (Neumann-folded: thA[0] = 0, thC[nTheta-1] = 0) and the 1/b' table, which takes 8 of the 20
-    // table bytes per cell out of the kernel's HBM stream. The factorisation is computed with exactly
-    // these rounded products (tridiag.cu), so factors and chunk products stay consistent.
-    float* thA;           // nTheta
-    float* thC;           // nTheta
-    int compactSolve;
 };
 
 // geometric phase: velPhi/velTheta (this) -> velPhiOut/velThetaOut (next)

@@ -93,9 +93,6 @@ __global__ void buildTablesKernel(GridParams g, SpectralTables t)
         const double cot = (double)cosT / 2.0 / (double)h / (double)sinT;
         t.triA[k] = (float)(1.0 / h2 - cot);
         t.triC[k] = (float)(1.0 / h2 + cot);
-        // Neumann fold of the off-diagonals for n != 0, kernel/KaminoSolver.cu:139-153
-        t.thA[k] = (k == 0) ? 0.0f : t.triA[k];
-        t.thC[k] = (k == g.nTheta - 1) ? 0.0f : t.triC[k];
         t.sinSq[k] = __fmul_rn(sinT, sinT);
         // geometricFillKernel, kernel/KaminoCore.cu:494
         t.geoG[k] = __fdiv_rn(__fmul_rn(g.dt, cosT), __fmul_rn(g.radius, sinT));
@@ -315,7 +312,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 
 size_t spectralTableBytes(const GridParams& g)
 {
-    return sizeof(float2) * g.nPhi + sizeof(float) * 12 * g.nTheta + sizeof(float) * solveTableFloats(g) + 256 * 20;
+    return sizeof(float2) * g.nPhi + sizeof(float) * 10 * g.nTheta + sizeof(float) * solveTableFloats(g) + 256 * 18;
 }
 
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream)

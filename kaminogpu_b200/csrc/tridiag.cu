@@ -23,6 +23,11 @@
 // CR), so the pressure differs from the reference's by the reference's rounding error; the
 // parity tests bound it through the fp64 operator.
 //
+// Tried and rejected (r01n A/B): dropping the l and h tables and rebuilding the multipliers in the
+// kernel from per-row off-diagonals and the 1/b' table (8 of the 20 table bytes per cell less HBM
+// traffic) -- 53.0 us instead of 50.8 us at 2048 x 4096: with one 512-thread block per SM the kernel
+// is bound by the latency of its load phases, not by bandwidth, and the extra dependent loads cost more.
+//
 // Layout: the half spectrum is solved in place in its [theta][slot] layout (no transposes).
 // A block owns W consecutive wavenumber slots and P * W threads (thread = chunk p, system w).
 // Tables are [slot group][row][w] so that every access of a warp is a run of W floats.
@@ -72,31 +77,26 @@ __global__ void buildSolveTablesKernel(GridParams g, SpectralTables t, int W, in
     const int P = nT / L;
 
     // forward: l_i, 1/b'_i, h_i and beta_i = prod_{m = chunk start .. i} (-l_m) (from the ROUNDED l)
-    const bool compact = t.compactSolve != 0;
     double bPrev = 1.0, cPrev = 0.0, beta = 1.0;
-    float invbPrev32 = 1.0f;
     for (int i = 0; i < nT; ++i) {
         // coefficients exactly as precomputeABCKernel builds them, kernel/KaminoSolver.cu:128-153
         float a = t.triA[i], c = t.triC[i];
         float b = (float)(t.minusTwoOverH2 - (double)__fdiv_rn(nSq, t.sinSq[i]));
         if (i == 0) { b = __fadd_rn(b, a); a = 0.0f; }
         if (i == nT - 1) { b = __fadd_rn(b, c); c = 0.0f; }
-        // compact mode: the multipliers the kernel will form in fp32 from a_i, c_i and the rounded 1/b',
-        // and the pivots that follow from exactly those multipliers
-        const float l32 = compact ? __fmul_rn(a, invbPrev32) : (float)((i == 0) ? 0.0 : (double)a / bPrev);
-        const double bp = compact ? (double)b - (double)l32 * cPrev
-                                  : (double)b - ((i == 0) ? 0.0 : (double)a / bPrev) * cPrev;
+        const double l = (i == 0) ? 0.0 : (double)a / bPrev;
+        const double bp = (double)b - l * cPrev;
+        const float l32 = (float)l;
         const double invb = 1.0 / bp;
-        const float invb32 = (float)invb;
         if (i % L == 0) beta = 1.0;
         beta *= -(double)l32;
         const size_t e = base + (size_t)i * W;
         t.thL[e] = l32;
-        t.thInvB[e] = invb32;
+        t.thInvB[e] = (float)invb;
         t.thBetaInv[e] = (float)(beta * invb);
-        t.thH[e] = compact ? __fmul_rn(c, invb32) : (float)((double)c * invb);
+        t.thH[e] = (float)((double)c * invb);
         if (i % L == L - 1) t.thBetaEnd[((size_t)(slot / W) * P + i / L) * W + (slot % W)] = (float)beta;
-        bPrev = bp; cPrev = (double)c; invbPrev32 = invb32;
+        bPrev = bp; cPrev = (double)c;
     }
     // backward: delta_i = prod_{m = i .. chunk end} (-h_m) (from the ROUNDED h)
     double delta = 1.0;
@@ -147,18 +147,10 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
     constexpr int kPre = kPrefetch ? L : 1;
     constexpr int kBatch = L < 16 ? L : 16;             // items per thread per load / store batch
     const int row0 = p * L;
-    const bool compact = t.compactSolve != 0;
     float lReg[kPre];
     if (kPrefetch) {
-        if (compact) {
-            // l_i = a_i / b'_{i-1} as a_i * (1/b'_{i-1}); row -1 does not exist and a_0 = 0
 #pragma unroll
-            for (int ii = 0; ii < L; ++ii)
-                lReg[ii] = __fmul_rn(__ldg(t.thA + row0 + ii), __ldg(tabInvB + max(row0 + ii - 1, 0) * W + w));
-        } else {
-#pragma unroll
-            for (int ii = 0; ii < L; ++ii) lReg[ii] = __ldg(tabL + (row0 + ii) * W + w);
-        }
+        for (int ii = 0; ii < L; ++ii) lReg[ii] = __ldg(tabL + (row0 + ii) * W + w);
     }
     betaEnd[tid] = __ldg(t.thBetaEnd + (size_t)group * P * W + tid);
     deltaStart[tid] = __ldg(tabDelta + row0 * W + w);
@@ -188,9 +180,7 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
         float2 prev = make_float2(0.0f, 0.0f);
 #pragma unroll(kPrefetch ? L : 8)
         for (int ii = 0; ii < L; ++ii) {
-            const float l = kPrefetch ? lReg[ii]
-                          : compact ? __fmul_rn(__ldg(t.thA + row0 + ii), __ldg(tabInvB + max(row0 + ii - 1, 0) * W + w))
-                                    : __ldg(tabL + (row0 + ii) * W + w);
+            const float l = kPrefetch ? lReg[ii] : __ldg(tabL + (row0 + ii) * W + w);
             float2 v = mine[ii * W];
             v.x = __fmaf_rn(-l, prev.x, v.x);
             v.y = __fmaf_rn(-l, prev.y, v.y);
@@ -206,7 +196,7 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
             const int e = (row0 + ii) * W + w;
             invB[ii] = __ldg(tabInvB + e);
             betaInv[ii] = __ldg(tabBetaInv + e);
-            hReg[ii] = compact ? __fmul_rn(__ldg(t.thC + row0 + ii), invB[ii]) : __ldg(tabH + e);
+            hReg[ii] = __ldg(tabH + e);
         }
     }
     __syncthreads();
@@ -234,7 +224,7 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
             const int e = (row0 + ii) * W + w;
             const float ib = kPrefetch ? invB[ii] : __ldg(tabInvB + e);
             const float bi = kPrefetch ? betaInv[ii] : __ldg(tabBetaInv + e);
-            const float hh = kPrefetch ? hReg[ii] : compact ? __fmul_rn(__ldg(t.thC + row0 + ii), ib) : __ldg(tabH + e);
+            const float hh = kPrefetch ? hReg[ii] : __ldg(tabH + e);
             float2 v = mine[ii * W];
             v.x = __fmaf_rn(bi, yPrev.x, __fmul_rn(v.x, ib));
             v.y = __fmaf_rn(bi, yPrev.y, __fmul_rn(v.y, ib));
