@@ -22,6 +22,8 @@
 //   inverse : row j needs p_j (for the phi gradient) and p_{j+1} - p_j (for the theta
 //             gradient). By linearity both come from one transform of X + iY with
 //             X = U_j, Y = U_{j+1} - U_j, so no block ever needs another block's output.
+#include <cstdlib>
+
 #include "kamino_kernels.cuh"
 #include "fft_core.cuh"
 #include "tma_bulk.cuh"
@@ -142,8 +144,8 @@ __device__ __forceinline__ uint64_t* stageTwiddles(const float2* __restrict__ tw
 // Each transform handles a pair of theta rows (z = div_j + i div_{j+1}) with T = N/16 threads;
 // a block of BLOCK threads holds BLOCK/T transforms. grid (ceil(nTheta/2 / (BLOCK/T)), batch),
 // dynamic smem: [twiddles N float2 if STAGE] + (BLOCK/T) * paddedSize(N) float2.
-template <int BLOCK, bool STAGE>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, bool STAGE, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ velPhiAll,
                     const float* __restrict__ velThetaAll, float2* __restrict__ spectrumAll)
 {
@@ -227,8 +229,8 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
 
 // One transform per theta row with T = N/16 threads, BLOCK/T rows per block.
 // grid (ceil(nTheta / (BLOCK/T)), batch), dynamic smem as for the forward kernel.
-template <int BLOCK, bool STAGE>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, bool STAGE, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restrict__ spectrumAll,
                          float* __restrict__ velPhiAll, float* __restrict__ velThetaAll,
                          float* __restrict__ pressureAll)
@@ -339,23 +341,29 @@ FftLaunch fftLaunch(const GridParams& g)
     return l;
 }
 
-template <int BLOCK, bool STAGE>
+int fftMinBlocks()
+{
+    static const int v = [] { const char* e = getenv("KAMINO_FFT_MINBLOCKS"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+template <int BLOCK, bool STAGE, int MINB>
 cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
                         const float* velPhiIn, const float* velThetaIn, float2* spectrum,
                         float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream)
 {
     if (which == 0) {           // configure
-        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
     }
     if (which == 1) {
         const int pairs = g.rowCount / 2;
         dim3 grid((pairs + l.perBlock - 1) / l.perBlock, batch);
-        return launchChained(divergenceFFTKernel<BLOCK, STAGE>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum);
+        return launchChained(divergenceFFTKernel<BLOCK, STAGE, MINB>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum);
     } else {
         dim3 grid((g.rowCount + l.perBlock - 1) / l.perBlock, batch);
-        return launchChained(inverseFFTGradientKernel<BLOCK, STAGE>, grid, dim3(BLOCK), l.smem, stream, g, t,
+        return launchChained(inverseFFTGradientKernel<BLOCK, STAGE, MINB>, grid, dim3(BLOCK), l.smem, stream, g, t,
                              (const float2*)spectrum, velPhi, velTheta, pressure);
     }
 }
@@ -365,11 +373,14 @@ cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, c
                       float* pressure, int batch, cudaStream_t stream)
 {
     const FftLaunch l = fftLaunch(g);
-#define KB_FFT(B, S) return fftDispatch<B, S>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream)
+#define KB_FFT(B, S) return fftDispatch<B, S, 1>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream)
     switch (l.block) {
     case 64: if (l.stage) KB_FFT(64, true); else KB_FFT(64, false);
     case 128: KB_FFT(128, true);
-    case 256: KB_FFT(256, true);
+    case 256:
+        // experiment switch: KAMINO_FFT_MINBLOCKS=3 caps the registers at 80 (three 256-thread blocks per SM)
+        if (fftMinBlocks() == 3) return fftDispatch<256, true, 3>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream);
+        KB_FFT(256, true);
     case 512: KB_FFT(512, false);
     case 1024: KB_FFT(1024, false);
     default: return cudaErrorInvalidValue;
