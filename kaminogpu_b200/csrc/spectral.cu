@@ -373,7 +373,7 @@ cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, c
                       float* pressure, int batch, cudaStream_t stream)
 {
     const FftLaunch l = fftLaunch(g);
-#define KB_FFT(B, S) return fftDispatch<B, S, 1>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream)
+#define KB_FFT(B, S) return fftDispatch<B, S, 0>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream)
     switch (l.block) {
     case 64: if (l.stage) KB_FFT(64, true); else KB_FFT(64, false);
     case 128: KB_FFT(128, true);
