@@ -58,3 +58,33 @@ def test_missing_or_undecodable_image_is_reported(tool, tmp_path):
     junk = tmp_path / "junk.png"
     junk.write_bytes(b"not an image")
     assert subprocess.run([tool, str(junk), "16", out]).returncode == 3
+
+
+def test_particle_colours_follow_the_image(built, golden, tmp_path):
+    """KaminoParticles(path, ...): colorBGR = (G, R, B) / 255 of the mirrored, resized image at the
+    particle's cell (kernel/KaminoParticles.cu:56-72); positions from the rand()-driven lattice."""
+    exe = str(tmp_path / "particle_colour_check")
+    host = os.path.join(ROOT, "kaminogpu_b200", "host")
+    build = subprocess.run(["g++", "-std=c++17", "-O2", "-DKAMINO_HAVE_ZLIB", "-I" + os.path.join(ROOT, "include"), "-I" + host,
+                            "-o", exe, os.path.join(ROOT, "tests", "native", "particle_colour_check.cpp"),
+                            os.path.join(host, "KaminoParticles.cpp"), os.path.join(host, "KaminoQuantity.cpp"), os.path.join(host, "ImageIO.cpp"),
+                            "-L" + os.path.join(ROOT, "kaminogpu_b200"), "-lkamino_b200", "-lz",
+                            "-Wl,-rpath," + os.path.join(ROOT, "kaminogpu_b200")], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    nTheta, density = 32, 4.0
+    out = str(tmp_path / "particles.bin")
+    run = subprocess.run([exe, os.path.join(GOLDEN, "images", "smooth.png"), str(nTheta), str(density), out],
+                         capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    raw = open(out, "rb").read()
+    n = int(np.frombuffer(raw[:8], dtype=np.int64)[0])
+    assert n == 64 * 128                                      # numTheta = sqrt(4) * 32, numPhi = 2 numTheta
+    coords = np.frombuffer(raw[8:8 + 8 * n], dtype=np.float32).reshape(n, 2)
+    colours = np.frombuffer(raw[8 + 8 * n:], dtype=np.float32).reshape(n, 3)
+    image = golden["smooth.png.32x64"]                        # [theta][phi][B, G, R]
+    h = np.float32(np.pi / nTheta)
+    x = np.minimum(np.floor(coords[:, 0] / h).astype(np.int64), 2 * nTheta - 1)
+    y = np.minimum(np.floor(coords[:, 1] / h).astype(np.int64), nTheta - 1)
+    px = image[y, x].astype(np.float64) / 255.0
+    want = np.stack([px[:, 1], px[:, 2], px[:, 0]], axis=1).astype(np.float32)
+    assert np.array_equal(colours.view(np.uint32), want.view(np.uint32))
