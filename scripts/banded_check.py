@@ -60,10 +60,16 @@ def main():
             ref.sync()
             single = (time.perf_counter() - t1) / steps
         for name, a, b in (("velPhi", U, ru), ("velTheta", V, rv), ("density", RHO, rr)):
-            same = np.array_equal(a, b)
+            # bit patterns, so that runs which have gone non-finite still compare (at 8192 x 16384 the
+            # reference scheme's 1 / (h sin(theta)) pressure gradient amplifies fp32 noise ~1e7 x in the
+            # polar rows: the CPU oracle shows max|u_phi| 0.09 -> 26 -> 52 -> 104 over the first steps)
+            a32, b32 = np.ascontiguousarray(a, np.float32).view(np.uint32), np.ascontiguousarray(b, np.float32).view(np.uint32)
+            same = np.array_equal(a32, b32)
             ok &= same
-            print("banded x%d vs single GPU, %d x %d, %d steps: %-8s %s" % (world, nT, N, 2 + steps, name,
-                  "bit-identical" if same else "DIFFERS (max abs %.3e)" % np.abs(a - b).max()))
+            finite = float(np.isfinite(b).mean())
+            print("banded x%d vs single GPU, %d x %d, %d steps: %-8s %s (%.4f of the single-GPU values finite)" % (
+                  world, nT, N, 2 + steps, name,
+                  "bit-identical" if same else "DIFFERS in %d words" % int((a32 != b32).sum()), finite))
         print("banded x%d: %.3f ms/step   single GPU: %.3f ms/step" % (world, el / steps * 1e3, single * 1e3))
     s.close()
     dist.destroy_process_group()
