@@ -1,5 +1,7 @@
 #include "Kamino.h"
 
+#include <cstdlib>
+
 #include "KaminoTimer.h"
 
 Kamino::Kamino(fReal radius, size_t nTheta, fReal particleDensity,
@@ -26,14 +28,26 @@ void Kamino::run()
 
     const bool writeGrid = !(gridPath.empty() || gridPath == "null");
     const bool writeParticles = !(particlePath.empty() || particlePath == "null");
-    if (writeGrid) solver.write_data_bgeo(gridPath, 0);
-    if (writeParticles) solver.write_particles_bgeo(particlePath, 0);
+
+    // Checkpoint / restart (additions; the reference cannot resume a run): KAMINO_CHECKPOINT=<file>
+    // rewrites <file> after every frame, KAMINO_RESTART=<file> resumes after the frame it holds.
+    // A resumed run continues bit for bit (the state is raw fp32, T restarts from i * DT as the loop sets it).
+    const char* checkpointPath = std::getenv("KAMINO_CHECKPOINT");
+    const char* restartPath = std::getenv("KAMINO_RESTART");
+    int firstFrame = 1;
+    if (restartPath && restartPath[0]) {
+        firstFrame = (int)solver.read_checkpoint(restartPath) + 1;
+        std::cout << "Resuming after frame " << firstFrame - 1 << " from " << restartPath << std::endl;
+    } else {
+        if (writeGrid) solver.write_data_bgeo(gridPath, 0);
+        if (writeParticles) solver.write_particles_bgeo(particlePath, 0);
+    }
 
     KaminoTimer timer(solver.context());
     timer.startTimer();
 
-    float T = 0.0;
-    for (int i = 1; i <= frames; i++) {
+    float T = (firstFrame - 1) * DT;
+    for (int i = firstFrame; i <= frames; i++) {
         while (T < i * DT) {
             solver.stepForward(dt);
             T += dt;
@@ -44,9 +58,10 @@ void Kamino::run()
         std::cout << "Frame " << i << " is ready" << std::endl;
         if (writeGrid) solver.write_data_bgeo(gridPath, i);
         if (writeParticles) solver.write_particles_bgeo(particlePath, i);
+        if (checkpointPath && checkpointPath[0]) solver.write_checkpoint(checkpointPath, (unsigned)i);
     }
 
     float gpu_time = timer.stopTimer();
     std::cout << "Time spent: " << gpu_time << "ms" << std::endl;
-    std::cout << "Performance: " << 1000.0 * frames / gpu_time << " frames per second" << std::endl;
+    std::cout << "Performance: " << 1000.0 * (frames - firstFrame + 1) / gpu_time << " frames per second" << std::endl;
 }

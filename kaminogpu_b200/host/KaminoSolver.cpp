@@ -1,9 +1,11 @@
 #include "KaminoSolver.h"
 #include "ImageIO.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "BgeoWriter.h"
+#include "Checkpoint.h"
 
 // kernel/KaminoSolver.cu:12-67: the device allocations, the tridiagonal coefficient
 // tables and the FFT plan of the reference's constructor are all inside kamino_create.
@@ -123,6 +125,65 @@ void KaminoSolver::stepForward(fReal timeStep)
 }
 
 void KaminoSolver::synchronize() { KAMINO_CHECK(ctx, kamino_sync(ctx)); }
+
+// Raw checkpoint (no reference counterpart). State = u_phi, u_theta, density, particle
+// coordinates; dense host arrays in the field layouts of include/kamino_b200.h.
+void KaminoSolver::write_checkpoint(const std::string& path, unsigned frame)
+{
+    synchronize();
+    velPhi->copyBackToCPU();
+    velTheta->copyBackToCPU();
+    density->copyBackToCPU();
+    CheckpointState st;
+    st.header.nTheta = (uint32_t)nTheta;
+    st.header.nPhi = (uint32_t)nPhi;
+    st.header.radius = radius;
+    st.header.dt = frameDuration;
+    st.header.frame = frame;
+    st.header.stepsTaken = stepsTaken;
+    st.header.numParticles = particles ? particles->numOfParticles : 0;
+    st.velPhi.assign(velPhi->hostData(), velPhi->hostData() + nPhi * nTheta);
+    st.velTheta.assign(velTheta->hostData(), velTheta->hostData() + nPhi * (nTheta - 1));
+    st.density.assign(density->hostData(), density->hostData() + nPhi * nTheta);
+    if (particles && particles->numOfParticles) {
+        particles->copyBack2CPU();
+        st.particles.assign(particles->coordCPUBuffer, particles->coordCPUBuffer + 2 * particles->numOfParticles);
+    }
+    std::string error;
+    if (!writeCheckpoint(path, st, &error)) {
+        std::cerr << error << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+}
+
+unsigned KaminoSolver::read_checkpoint(const std::string& path)
+{
+    CheckpointState st;
+    std::string error;
+    if (!readCheckpoint(path, st, &error)) {
+        std::cerr << error << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    const size_t have = particles ? particles->numOfParticles : 0;
+    if (st.header.nTheta != nTheta || st.header.nPhi != nPhi || st.header.radius != radius
+        || st.header.dt != frameDuration || st.header.numParticles != have) {
+        std::cerr << "checkpoint: " << path << " was written by a run of a different shape, radius, dt or particle count" << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    synchronize();
+    std::copy(st.velPhi.begin(), st.velPhi.end(), velPhi->hostData());
+    std::copy(st.velTheta.begin(), st.velTheta.end(), velTheta->hostData());
+    std::copy(st.density.begin(), st.density.end(), density->hostData());
+    velPhi->copyToGPU();
+    velTheta->copyToGPU();
+    density->copyToGPU();
+    if (have) {
+        std::copy(st.particles.begin(), st.particles.end(), particles->coordCPUBuffer);
+        particles->copy2GPU();
+    }
+    stepsTaken = (size_t)st.header.stepsTaken;
+    return st.header.frame;
+}
 
 namespace {
 

@@ -58,6 +58,11 @@ public:
     KaminoParticles* particles;
 
     /* additions over the reference surface */
+    /* raw checkpoint / restart (Checkpoint.h): the complete state between two steps; `frame` is the
+       caller's position in its frame loop. Both synchronise. read_checkpoint exits (the reference's
+       error convention) on an unreadable file or a shape / dt / radius / particle-count mismatch. */
+    void write_checkpoint(const std::string& path, unsigned frame);
+    unsigned read_checkpoint(const std::string& path);
     void setPhaseTiming(bool on) { phaseTiming = on; }   // default: env KAMINO_PHASE_TIMERS=1
     void synchronize();
     kamino_ctx* context() { return ctx; }

@@ -572,6 +572,41 @@ def test_cli_image_driven_initialisation(K, tmp_path):
     assert parts["color"].shape == (2048, 3) and parts["color"].max() > 0.0      # particles are not black
 
 
+@pytest.mark.xfail(reason="written after this round's GPU budget was spent: not yet run on hardware", strict=False)
+def test_cli_restart_from_checkpoint_continues_bit_for_bit(K, tmp_path):
+    """KAMINO_CHECKPOINT / KAMINO_RESTART (raw state checkpoint): frames 1-2 with a
+    checkpoint, then a second process resuming for frames 3-4, must write the bytes an uninterrupted
+    4-frame run writes."""
+    import gzip
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "kaminogpu_b200", "kamino")
+
+    def run(tag, frames, env_extra):
+        d = tmp_path / tag
+        d.mkdir()
+        cfg = d / "configKamino.txt"
+        cfg.write_text("5.0 32 4.0 0.005 0.041666668 %d 0.0 1 1 1 1 %s/f %s/p null null null\n" % (frames, d, d))
+        out = subprocess.run([exe, str(cfg)], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env_extra))
+        assert out.returncode == 0, out.stderr
+        return d, out.stdout
+
+    whole, _ = run("whole", 4, {})
+    ck = str(tmp_path / "state.ck")
+    first, _ = run("first", 2, {"KAMINO_CHECKPOINT": ck})
+    assert os.path.exists(ck)
+    # the resumed run uses the same output directory layout; only frames 3 and 4 are written by it
+    second, stdout = run("second", 4, {"KAMINO_RESTART": ck})
+    assert "Resuming after frame 2" in stdout
+    for stem in ("f", "p"):
+        for frame in (1, 2):
+            assert gzip.open(str(first / ("%s%d.bgeo" % (stem, frame)))).read() == gzip.open(str(whole / ("%s%d.bgeo" % (stem, frame)))).read()
+        for frame in (3, 4):
+            assert gzip.open(str(second / ("%s%d.bgeo" % (stem, frame)))).read() == gzip.open(str(whole / ("%s%d.bgeo" % (stem, frame)))).read()
+        assert not os.path.exists(str(second / ("%s0.bgeo" % stem)))
+
+
 def test_forked_particles_mode_is_bit_identical(K, tmp_path):
     """KAMINO_FORK_PARTICLES=1 (particles as their own kernel on a parallel graph branch, three
     rotating velocity buffers) must produce the bits of the default fused launch."""
