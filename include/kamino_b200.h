@@ -141,6 +141,17 @@ int kamino_band_divergence_fft(kamino_ctx* ctx, int rowBegin, int rowCount);
 /* theta solve of slots [slotBegin, slotBegin+slotCount) (multiples of 8) for ALL rows, in place
  * on a packed device buffer [nTheta][pitch] of float2 (what the all-to-all delivers). */
 int kamino_band_tridiagonal(kamino_ctx* ctx, void* packedSpectrum, int pitch, int slotBegin, int slotCount);
+/* Reduced-interface ("SPIKE") alternative to the all-to-all around the theta solve (SURVEY.md 8f-3;
+ * no reference counterpart). prepare builds, once, the LU factors of the rank's band
+ * [rowBegin, rowBegin+rowCount) (a power of two >= 16 rows) cut loose from the neighbouring bands;
+ * local_solve applies them in place to the spectrum rows of the band, all wavenumbers, with the
+ * same kernel as the full solve. The driver (kaminogpu_b200/banded.py) derives the spike vectors
+ * from unit right-hand sides, exchanges two interface values per wavenumber and rank, and corrects
+ * the band. tridiagonal_coefficients returns the unfolded sub- and super-diagonal of a row
+ * (kernel/KaminoSolver.cu:135-138), i.e. the couplings across a band boundary. */
+int kamino_band_solver_prepare(kamino_ctx* ctx, int rowBegin, int rowCount);
+int kamino_band_local_solve(kamino_ctx* ctx);
+int kamino_tridiagonal_coefficients(kamino_ctx* ctx, int row, float* subDiagonal, float* superDiagonal);
 /* inverse FFT + gradient subtraction of rows [rowBegin, rowBegin+rowCount); reads spectrum rows
  * rowBegin .. rowBegin+rowCount (one past the band, unless it is the last row of the grid). */
 int kamino_band_inverse_fft_gradient(kamino_ctx* ctx, int rowBegin, int rowCount);

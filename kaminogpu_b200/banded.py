@@ -108,7 +108,117 @@ class BandLayout:
         return self.spectrum[j]
 
 
-class BandRank(BandLayout):
+# ---- reduced-interface ("SPIKE") theta solve: no transposes, one small all-gather per step --------------
+#
+# Every wavenumber's theta system A x = d is tridiagonal over ALL rows, which is why the default mode
+# transposes the half spectrum with two all-to-alls (2 x nTheta x nPhi/2 x 8 bytes per step: 2 x 537 MB at
+# 8192 x 16384). Splitting the rows into the P bands,
+#     A_p x_p + a_lo x_(lo-1) e_first + c_(hi-1) x_hi e_last = d_p ,
+# so with g_p = A_p^-1 d_p (one band-local solve per step) and the right-hand-side independent spikes
+# v_p = A_p^-1 (a_lo e_first), w_p = A_p^-1 (c_(hi-1) e_last) (computed once),
+#     x_p = g_p - v_p x_(lo-1) - w_p x_hi .
+# Taking the first and last row of that identity for every band gives a 2P x 2P system per wavenumber
+# in the interface values (t_p, b_p) = (x_lo, x_(hi-1)); its matrix does not depend on the right-hand
+# side, so its inverse is computed once (fp64) and a step needs: the local solve, an all-gather of two
+# rows of the band's half spectrum per rank (2 x nPhi/2 x 8 bytes: 131 KB at 8192 x 16384), one small
+# matrix-vector product per wavenumber and one fused correction of the band. x_hi = t_(p+1) also
+# provides the extra spectrum row the theta gradient of the last band row needs. The result equals the
+# global solve up to round-off (tests/test_banded_comm_cpu.py: 1e-11 against a direct fp64 solve), but
+# it is a different operation order than the single-GPU kernel, so this mode is compared at tolerance
+# level, not bit for bit; the band-local solves run the kernel of the full solve at nTheta / P rows.
+class SpikeInterface:
+    """The communication / algebra part, over torch tensors (GPU ranks and the CPU stand-in alike).
+
+    Needs from the host object: rank, world, lo, hi, spectrum [nTheta][half][2], local_solve() (in place
+    on spectrum[lo:hi]), coupling() -> (a_lo, c_hi_minus_1) (0.0 where the band touches a pole)."""
+
+    # The two collectives are kept out of the phase methods so that the same code serves the NCCL run,
+    # the gloo stand-in and the virtual ranks of LocalGroup (which gathers by plain copies).
+    def spike_setup_local(self):
+        """Spikes of my band from two unit right-hand sides; returns my four interface rows [4][half]."""
+        torch = self.torch
+        band = self.spectrum[self.lo:self.hi]
+        m = band.shape[0]
+        a_lo, c_hi = self.coupling()
+        saved = band.clone()
+        spikes = []
+        for row, coeff in ((0, a_lo), (m - 1, c_hi)):
+            band.zero_()
+            if coeff != 0.0:
+                band[row, :, 0] = coeff
+                self.local_solve()
+            spikes.append(band[:, :, 0].clone())
+        band.copy_(saved)
+        self.spike_v, self.spike_w = spikes                       # [m][half]
+        return torch.stack([self.spike_v[0], self.spike_v[m - 1], self.spike_w[0], self.spike_w[m - 1]]).contiguous()
+
+    def spike_setup_finish(self, everyone):
+        """everyone[p] = rank p's interface rows (v_first, v_last, w_first, w_last)."""
+        torch = self.torch
+        band = self.spectrum[self.lo:self.hi]
+        half, P = band.shape[1], self.world
+        device = band.device
+        M = torch.zeros((half, 2 * P, 2 * P), dtype=torch.float64, device=device)
+        eye = torch.arange(2 * P, device=device)
+        M[:, eye, eye] = 1.0
+        for p in range(P):
+            vt, vb, wt, wb = (everyone[p][k].to(torch.float64) for k in range(4))
+            if p > 0:
+                M[:, 2 * p, 2 * p - 1] = vt
+                M[:, 2 * p + 1, 2 * p - 1] = vb
+            if p < P - 1:
+                M[:, 2 * p, 2 * p + 2] = wt
+                M[:, 2 * p + 1, 2 * p + 2] = wb
+        self.reduced_inverse = torch.linalg.inv(M)                 # [half][2P][2P], fp64
+        self._interface = torch.empty((2, half, 2), dtype=band.dtype, device=device)
+
+    def spike_local(self):
+        """Band-local solve in place (band <- g); returns my interface rows [2][half][2] (first, last)."""
+        band = self.spectrum[self.lo:self.hi]
+        self.local_solve()
+        self._interface[0].copy_(band[0])
+        self._interface[1].copy_(band[band.shape[0] - 1])
+        return self._interface
+
+    def spike_finish(self, gathered):
+        """gathered[p] = rank p's interface rows. Solves the reduced system and corrects the band;
+        spectrum[hi] (if the band is not the last one) receives the solution's next row."""
+        torch = self.torch
+        band = self.spectrum[self.lo:self.hi]
+        P, p = self.world, self.rank
+        # right-hand side of the reduced system: [half][2P][re/im], unknown order t_0, b_0, t_1, b_1, ...
+        rhs = torch.stack([g[k] for g in gathered for k in (0, 1)], dim=1).to(torch.float64)
+        z = torch.matmul(self.reduced_inverse, rhs)                # [half][2P][2]
+        zero = torch.zeros_like(z[:, 0])
+        above = z[:, 2 * p - 1] if p > 0 else zero                 # x_(lo-1) = b_(p-1)
+        below = z[:, 2 * p + 2] if p < P - 1 else zero             # x_hi     = t_(p+1)
+        above, below = above.to(band.dtype), below.to(band.dtype)
+        band.sub_(self.spike_v[:, :, None] * above[None] + self.spike_w[:, :, None] * below[None])
+        if p < P - 1:
+            self.spectrum[self.hi].copy_(below)
+
+    # ---- with a torch.distributed-style process group ---------------------------------------------------
+    def spike_setup(self, dist):
+        mine = self.spike_setup_local()
+        everyone = [self.torch.empty_like(mine) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(everyone, mine)
+        else:
+            everyone[0] = mine
+        self.spike_setup_finish(everyone)
+        self._gathered = [self.torch.empty_like(self._interface) for _ in range(self.world)]
+
+    def spike_solve(self, dist):
+        """spectrum[lo:hi] holds the right-hand sides on entry and the solution on exit."""
+        mine = self.spike_local()
+        if self.world > 1:
+            dist.all_gather(self._gathered, mine)
+        else:
+            self._gathered[0].copy_(mine)
+        self.spike_finish(self._gathered)
+
+
+class BandRank(BandLayout, SpikeInterface):
     """The state and compute phases of one rank (no communication in here)."""
 
     def __init__(self, nTheta, radius, dt, rank, world, device=0):
@@ -165,6 +275,22 @@ class BandRank(BandLayout):
     def inverse(self):
         capi.check(self.lib.kamino_band_inverse_fft_gradient(self.ctx, self.lo, self.hi - self.lo), self.ctx)
 
+    # ---- reduced-interface (SPIKE) mode: see SpikeInterface ---------------------------------------------
+    def prepare_local_solver(self):
+        capi.check(self.lib.kamino_band_solver_prepare(self.ctx, self.lo, self.hi - self.lo), self.ctx)
+
+    def local_solve(self):
+        capi.check(self.lib.kamino_band_local_solve(self.ctx), self.ctx)
+
+    def coupling(self):
+        """(a of my first row, c of my last row): the couplings to the neighbouring bands, 0 at the poles."""
+        a, c = ctypes.c_float(0.0), ctypes.c_float(0.0)
+        if self.lo > 0:
+            capi.check(self.lib.kamino_tridiagonal_coefficients(self.ctx, self.lo, ctypes.byref(a), None), self.ctx)
+        if self.hi < self.nTheta:
+            capi.check(self.lib.kamino_tridiagonal_coefficients(self.ctx, self.hi - 1, None, ctypes.byref(c)), self.ctx)
+        return float(a.value), float(c.value)
+
     # ---- host access (tests, start-up) ----------------------------------------------------------------
     def download_band(self):
         """numpy copies of my rows of u_phi, u_theta (clipped to nTheta-1 rows), density."""
@@ -205,8 +331,13 @@ def all_to_all(recv, send, dist):
 class DistributedBandedSolver:
     """One rank of a band-decomposed simulation under torch.distributed."""
 
-    def __init__(self, nTheta, radius, dt, device=0):
+    def __init__(self, nTheta, radius, dt, device=0, solve="alltoall"):
+        """solve = "alltoall" (default: transposes around the full theta solve, bit-identical to the
+        single-GPU step) or "spike" (reduced-interface solve, no transposes; see SpikeInterface)."""
         import torch.distributed as dist
+        if solve not in ("alltoall", "spike"):
+            raise ValueError("solve must be 'alltoall' or 'spike'")
+        self.solve = solve
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.r = BandRank(nTheta, radius, dt, self.rank, self.world, device)
@@ -216,6 +347,10 @@ class DistributedBandedSolver:
         self.stream = torch.cuda.Stream(device=torch.device("cuda", device))
         self.r.set_stream(self.stream.cuda_stream)
         self._graph, self._eager_done = None, 0      # None: not captured yet; False: capture unavailable
+        if solve == "spike" and self.world > 1:
+            with torch.cuda.stream(self.stream):
+                self.r.prepare_local_solver()
+                self.r.spike_setup(dist)
 
     def close(self):
         if self._graph:                       # release the captured NCCL work before the communicator goes away
@@ -275,6 +410,10 @@ class DistributedBandedSolver:
             if self.world > 1:
                 exchange(r.halo_sends(), r.halo_recvs(), dist)
             r.advect_to_spectrum()
+            if self.world > 1 and self.solve == "spike":
+                r.spike_solve(dist)
+                r.inverse()
+                continue
             if self.world > 1:
                 all_to_all(r.recv, r.pack_forward(), dist)
                 packed = r.recv
@@ -296,9 +435,19 @@ class DistributedBandedSolver:
 class LocalGroup:
     """P virtual ranks in one process on one GPU: the same phases, device copies instead of NCCL."""
 
-    def __init__(self, nTheta, radius, dt, world, device=0):
+    def __init__(self, nTheta, radius, dt, world, device=0, solve="alltoall"):
         self.ranks = [BandRank(nTheta, radius, dt, r, world, device) for r in range(world)]
         self.world = world
+        self.solve = solve
+        if solve == "spike" and world > 1:
+            for r in self.ranks:
+                r.prepare_local_solver()
+            self.sync()
+            rows = [r.spike_setup_local() for r in self.ranks]
+            self.sync()
+            for r in self.ranks:
+                r.spike_setup_finish(rows)
+            self.sync()
 
     def close(self):
         for r in self.ranks:
@@ -326,6 +475,15 @@ class LocalGroup:
             for r in R:
                 r.advect_to_spectrum()
             self.sync()
+            if self.solve == "spike" and self.world > 1:
+                rows = [r.spike_local().clone() for r in R]
+                self.sync()
+                for r in R:
+                    r.spike_finish(rows)
+                self.sync()
+                for r in R:
+                    r.inverse()
+                continue
             packs = [r.pack_forward() for r in R]
             self.sync()
             for r in R:

@@ -48,6 +48,9 @@ SIGNATURES = {
     "kamino_band_divergence_fft": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "kamino_band_tridiagonal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "kamino_band_inverse_fft_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kamino_band_solver_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kamino_band_local_solve": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_tridiagonal_coefficients": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p]),
     "kamino_spectrum_device_ptr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "kamino_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kamino_sync": (ctypes.c_int, [ctypes.c_void_p]),

@@ -46,6 +46,10 @@ struct kamino_ctx {
     float* snapshot = nullptr;           // staging for overlapped frame read-backs
     size_t snapshotFloats = 0;
     SpectralTables tables{};
+    // band-local LU tables of the reduced-interface (SPIKE) mode, built by kamino_band_solver_prepare
+    char* bandArena = nullptr;
+    SpectralTables bandTables{};
+    int bandRowBegin = 0, bandRows = 0;
 
     int velIdx = 0, densityIdx = 0, particleIdx = 0;   // which buffer is "this step"
     // Velocity buffers in rotation. advect writes next(v), geometric writes next(next(v)), the
@@ -466,6 +470,7 @@ int kamino_destroy(kamino_ctx* ctx)
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->particleArena) cudaFree(ctx->particleArena);
+    if (ctx->bandArena) cudaFree(ctx->bandArena);
     delete ctx;
     return 0;
 }
@@ -644,6 +649,56 @@ int kamino_band_tridiagonal(kamino_ctx* ctx, void* packedSpectrum, int pitch, in
     cudaError_t e = launchTridiagonalBand(ctx->g, ctx->tables, (float2*)packedSpectrum, pitch, slotBegin, slotCount,
                                           ctx->batch, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, (int)e, "kamino_band_tridiagonal (slot range must be a multiple of 8)");
+    return 0;
+}
+
+int kamino_band_solver_prepare(kamino_ctx* ctx, int rowBegin, int rowCount)
+{
+    GridParams g;
+    if (int rc = bandRange(ctx, rowBegin, rowCount, 16, &g)) return rc;
+    if (rowCount & (rowCount - 1)) return fail(ctx, KAMINO_ERR_INVALID, "the band-local solve needs a power-of-two row count");
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->bandArena) { cudaFree(ctx->bandArena); ctx->bandArena = nullptr; ctx->bandRows = 0; }
+    const size_t slotRows = (size_t)rowCount * (ctx->g.nPhi / 2);
+    const size_t endFloats = (size_t)(rowCount / 4 + 1) * (ctx->g.nPhi / 2);
+    const size_t bytes = alignUp(sizeof(float) * slotRows, 256) * 5 + alignUp(sizeof(float) * endFloats, 256);
+    KB_TRY(ctx, cudaMalloc((void**)&ctx->bandArena, bytes));
+    char* p = ctx->bandArena;
+    auto sub = [&p](size_t b) { char* r = p; p += alignUp(b, 256); return r; };
+    ctx->bandTables = ctx->tables;                  // per-row tables are shared; the th* members are the band's own
+    ctx->bandTables.thL = (float*)sub(sizeof(float) * slotRows);
+    ctx->bandTables.thInvB = (float*)sub(sizeof(float) * slotRows);
+    ctx->bandTables.thBetaInv = (float*)sub(sizeof(float) * slotRows);
+    ctx->bandTables.thH = (float*)sub(sizeof(float) * slotRows);
+    ctx->bandTables.thDelta = (float*)sub(sizeof(float) * slotRows);
+    ctx->bandTables.thBetaEnd = (float*)sub(sizeof(float) * endFloats);
+    cudaError_t e = launchBuildBandSolveTables(ctx->g, ctx->tables, ctx->bandTables, rowBegin, rowCount, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "kamino_band_solver_prepare");
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bandRowBegin = rowBegin;
+    ctx->bandRows = rowCount;
+    return 0;
+}
+
+int kamino_band_local_solve(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (ctx->bandRows == 0) return fail(ctx, KAMINO_ERR_STATE, "kamino_band_solver_prepare has not been called");
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = launchBandLocalSolve(ctx->g, ctx->bandTables, ctx->spectrum, ctx->bandRowBegin, ctx->bandRows, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "kamino_band_local_solve");
+    return 0;
+}
+
+int kamino_tridiagonal_coefficients(kamino_ctx* ctx, int row, float* subDiagonal, float* superDiagonal)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (row < 0 || row >= ctx->g.nTheta) return fail(ctx, KAMINO_ERR_INVALID, "row out of range");
+    DeviceGuard guard(ctx->device);
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (subDiagonal) KB_TRY(ctx, cudaMemcpy(subDiagonal, ctx->tables.triA + row, sizeof(float), cudaMemcpyDeviceToHost));
+    if (superDiagonal) KB_TRY(ctx, cudaMemcpy(superDiagonal, ctx->tables.triC + row, sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -97,6 +97,13 @@ cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, floa
 // `packed` as [theta][slot - slotBegin] with row pitch `pitch` (float2 elements), one simulation
 cudaError_t launchTridiagonalBand(const GridParams& g, const SpectralTables& t, float2* packed, int pitch,
                                   int slotBegin, int slotCount, int tableBatch, cudaStream_t stream);
+// band-local theta solve of the reduced-interface (SPIKE) mode: `band` holds th* tables built for rows
+// [rowBegin, rowBegin + rows) cut loose from their neighbours; only its th* members are used
+size_t bandSolveTableFloats(const GridParams& g, int rows);
+cudaError_t launchBuildBandSolveTables(const GridParams& g, const SpectralTables& t, const SpectralTables& band,
+                                       int rowBegin, int rows, cudaStream_t stream);
+cudaError_t launchBandLocalSolve(const GridParams& g, const SpectralTables& band, float2* spectrum, int rowBegin, int rows,
+                                 cudaStream_t stream);
 // velPhi / velTheta updated in place; pressure (may be NULL) receives p.
 cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
                                      float* velPhi, float* velTheta, float* pressure, int batch,

@@ -108,6 +108,52 @@ __global__ void buildSolveTablesKernel(GridParams g, SpectralTables t, int W, in
     }
 }
 
+// The same factorisation for ONE theta band of a band-decomposed run (reduced-interface / SPIKE solve,
+// banded.py): rows [rowBegin, rowBegin + rows) of every wavenumber's system, cut loose from the
+// neighbouring bands (the sub-diagonal of the first band row and the super-diagonal of the last one
+// are left out; the driver re-introduces them through the spike vectors). Global rows 0 and
+// nTheta - 1 keep the reference's Neumann fold. Tables are laid out as for a grid of `rows` rows.
+__global__ void buildBandSolveTablesKernel(GridParams g, SpectralTables t, SpectralTables band, int rowBegin, int rows, int W, int L)
+{
+    const int nT = g.nTheta, half = g.nPhi >> 1;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= half) return;
+    const int n = (slot == 0) ? half : slot;
+    const size_t base = (size_t)(slot / W) * rows * W + (slot % W);
+    const float nSq = (float)(n * n);
+    const int P = rows / L;
+    double bPrev = 1.0, cPrev = 0.0, beta = 1.0;
+    for (int i = 0; i < rows; ++i) {
+        const int gi = rowBegin + i;
+        float a = t.triA[gi], c = t.triC[gi];
+        float b = (float)(t.minusTwoOverH2 - (double)__fdiv_rn(nSq, t.sinSq[gi]));
+        if (gi == 0) { b = __fadd_rn(b, a); a = 0.0f; }
+        if (gi == nT - 1) { b = __fadd_rn(b, c); c = 0.0f; }
+        if (i == 0) a = 0.0f;                       // coupling to the band above: handled by the spikes
+        if (i == rows - 1) c = 0.0f;                // coupling to the band below
+        const double l = (i == 0) ? 0.0 : (double)a / bPrev;
+        const double bp = (double)b - l * cPrev;
+        const float l32 = (float)l;
+        const double invb = 1.0 / bp;
+        if (i % L == 0) beta = 1.0;
+        beta *= -(double)l32;
+        const size_t e = base + (size_t)i * W;
+        band.thL[e] = l32;
+        band.thInvB[e] = (float)invb;
+        band.thBetaInv[e] = (float)(beta * invb);
+        band.thH[e] = (float)((double)c * invb);
+        if (i % L == L - 1) band.thBetaEnd[((size_t)(slot / W) * P + i / L) * W + (slot % W)] = (float)beta;
+        bPrev = bp; cPrev = (double)c;
+    }
+    double delta = 1.0;
+    for (int i = rows - 1; i >= 0; --i) {
+        if (i % L == L - 1) delta = 1.0;
+        const size_t e = base + (size_t)i * W;
+        delta *= -(double)band.thH[e];
+        band.thDelta[e] = (float)delta;
+    }
+}
+
 // ---- per step -------------------------------------------------------------------------------------
 // grid ((N/2) / W, batch), P * W threads, dynamic smem (P (L W + W) + 2 (P + 1) W) float2 + 2 P W floats.
 // Shared-memory rows of the right-hand sides are padded by one W-run per chunk (pitch L*W + W):
@@ -329,6 +375,43 @@ cudaError_t launchTridiagonalBand(const GridParams& g, const SpectralTables& t, 
                                   int slotBegin, int slotCount, int tableBatch, cudaStream_t stream)
 {
     return dispatchTri(g, t, packed, 1, stream, false, tableBatch, pitch, slotBegin, slotCount);
+}
+
+// ---- band-local solve (reduced-interface / SPIKE mode of the band-decomposed run) -------------------
+
+namespace {
+GridParams bandSolveParams(const GridParams& g, int rows)
+{
+    GridParams b = g;
+    b.nTheta = rows;        // selects L, P and the kernel instantiation; nPhi (the slot count) is unchanged
+    return b;
+}
+} // namespace
+
+size_t bandSolveTableFloats(const GridParams& g, int rows)
+{
+    return (size_t)rows * (g.nPhi / 2) * 5 + (size_t)(rows / 4 + 1) * (g.nPhi / 2);
+}
+
+cudaError_t launchBuildBandSolveTables(const GridParams& g, const SpectralTables& t, const SpectralTables& band,
+                                       int rowBegin, int rows, cudaStream_t stream)
+{
+    const GridParams b = bandSolveParams(g, rows);
+    cudaError_t e = dispatchTri(b, band, nullptr, 1, nullptr, true, 1, g.nPhi / 2, 0, g.nPhi / 2);    // opt-in smem
+    if (e != cudaSuccess) return e;
+    const TriLaunch l = triLaunch(b, 1);
+    const int half = g.nPhi / 2, threads = 64;
+    buildBandSolveTablesKernel<<<(half + threads - 1) / threads, threads, 0, stream>>>(g, t, band, rowBegin, rows, l.W, l.L);
+    return cudaGetLastError();
+}
+
+// in place on spectrum rows [rowBegin, rowBegin + rows), all wavenumber slots
+cudaError_t launchBandLocalSolve(const GridParams& g, const SpectralTables& band, float2* spectrum, int rowBegin, int rows,
+                                 cudaStream_t stream)
+{
+    const GridParams b = bandSolveParams(g, rows);
+    const int half = g.nPhi / 2;
+    return dispatchTri(b, band, spectrum + (size_t)rowBegin * half, 1, stream, false, 1, half, 0, half);
 }
 
 } // namespace kb

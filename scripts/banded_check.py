@@ -2,7 +2,7 @@
 """Multi-GPU check of the theta-band mode (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/banded_check.py [nTheta] [steps]
+        scripts/banded_check.py [nTheta] [steps] [alltoall|spike]
 
 Every rank steps its band of ONE simulation (NCCL halo exchange + all-to-all); rank 0 also runs the
 ordinary single-GPU solver and the gathered bands must be bit-identical to it. Prints timings.
@@ -25,6 +25,7 @@ from kaminogpu_b200.solver import KaminoSolver         # noqa: E402
 def main():
     nT = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    solve = sys.argv[3] if len(sys.argv) > 3 else "alltoall"        # or "spike": reduced-interface theta solve
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -33,7 +34,7 @@ def main():
     h = np.float32(np.pi / nT)
     rho0 = (0.5 + 0.5 * np.sin(4.0 * ii * float(h)) * np.sin((jj + 0.5) * float(h)) ** 2).astype(np.float32)
     dt = 0.005 if nT <= 2048 else 0.0025
-    s = banded.DistributedBandedSolver(nT, 5.0, dt, device=local)
+    s = banded.DistributedBandedSolver(nT, 5.0, dt, device=local, solve=solve)
     s.r.solver.density.cpuBuffer[:] = rho0
     s.r.solver.density.copyToGPU()
     dist.barrier(); torch.cuda.synchronize()
@@ -65,11 +66,17 @@ def main():
             # polar rows: the CPU oracle shows max|u_phi| 0.09 -> 26 -> 52 -> 104 over the first steps)
             a32, b32 = np.ascontiguousarray(a, np.float32).view(np.uint32), np.ascontiguousarray(b, np.float32).view(np.uint32)
             same = np.array_equal(a32, b32)
-            ok &= same
+            if solve != "spike":
+                ok &= same
             finite = float(np.isfinite(b).mean())
             print("banded x%d vs single GPU, %d x %d, %d steps: %-8s %s (%.4f of the single-GPU values finite)" % (
                   world, nT, N, 2 + steps, name,
                   "bit-identical" if same else "DIFFERS in %d words" % int((a32 != b32).sum()), finite))
+            if solve == "spike":                # a different operation order: compared at tolerance level
+                fin = np.isfinite(a) & np.isfinite(b)
+                rel = float(np.linalg.norm((a - b)[fin]) / max(np.linalg.norm(b[fin]), 1e-30))
+                print("    spike mode: relative L2 difference %.2e" % rel)
+                ok &= rel <= 1e-3
         print("banded x%d: %.3f ms/step   single GPU: %.3f ms/step" % (world, el / steps * 1e3, single * 1e3))
     s.close()
     dist.destroy_process_group()

@@ -665,3 +665,36 @@ def test_banded_step_is_bit_identical_to_single_gpu(K, nT, world):
     assert np.array_equal(u.ravel(), ref["velPhi"])
     assert np.array_equal(v.ravel(), ref["velTheta"])
     assert np.array_equal(rho.ravel(), ref["density"])
+
+
+@pytest.mark.xfail(reason="written after this round's GPU budget was spent: the band-local solve has not run on hardware yet",
+                   strict=False)
+@pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
+def test_banded_spike_mode_tracks_single_gpu(K, nT, world):
+    """Reduced-interface (SPIKE) theta solve of the band-decomposed run (banded.SpikeInterface; band-local
+    LU solves + a 2P x 2P interface system per wavenumber instead of the two all-to-all transposes): same
+    systems, different operation order, so the comparison with the single-context step is at tolerance
+    level. Bars after 2 steps: density and u_theta 1e-5 relative L2; u_phi 2e-4 (the 1/(h sin(theta))
+    amplification of pressure round-off in the polar rows, as in the projection tests)."""
+    from kaminogpu_b200 import banded
+    N = 2 * nT
+    rho0 = oa.synthetic_density(nT).reshape(nT, N)
+    with K.KaminoSolver(N, nT, 5.0, 0.005) as s:
+        s.density.cpuBuffer[:] = rho0
+        s.density.copyToGPU()
+        s.stepForward(0.005, nSteps=2)
+        s.sync()
+        ref = state(s)
+    grp = banded.LocalGroup(nT, 5.0, 0.005, world, solve="spike")
+    try:
+        for r in grp.ranks:
+            r.solver.density.cpuBuffer[:] = rho0
+            r.solver.density.copyToGPU()
+        grp.step(2)
+        u, v, rho = grp.gather()
+    finally:
+        grp.close()
+    for name, got, tol in (("velPhi", u, 2e-4), ("velTheta", v, 1e-5), ("density", rho, 1e-5)):
+        err = oa.rel_l2(got.ravel(), ref[name])
+        print("banded spike x%d, nTheta %d: %-8s relL2 vs single GPU %.2e" % (world, nT, name, err))
+        assert err <= tol, name
