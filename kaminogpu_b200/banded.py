@@ -247,6 +247,7 @@ class BandRank(BandLayout, SpikeInterface):
 
     def set_stream(self, cuda_stream_ptr):
         self.solver.set_stream(cuda_stream_ptr)
+        self._kernels_on_torch_stream = True        # kernels and torch ops are ordered on one stream from here on
 
     def fields(self):
         """Full-size torch views of the this-step u_phi, u_theta, density (pointers move with the swaps)."""
@@ -280,7 +281,14 @@ class BandRank(BandLayout, SpikeInterface):
         capi.check(self.lib.kamino_band_solver_prepare(self.ctx, self.lo, self.hi - self.lo), self.ctx)
 
     def local_solve(self):
+        # the spike setup interleaves torch writes to the band with this kernel: unless both run on one
+        # stream (DistributedBandedSolver), order them through the host (LocalGroup's virtual ranks)
+        shared = getattr(self, "_kernels_on_torch_stream", False)
+        if not shared:
+            self.torch.cuda.synchronize()
         capi.check(self.lib.kamino_band_local_solve(self.ctx), self.ctx)
+        if not shared:
+            self.solver.sync()
 
     def coupling(self):
         """(a of my first row, c of my last row): the couplings to the neighbouring bands, 0 at the poles."""
