@@ -573,6 +573,7 @@ def test_cli_image_driven_initialisation(K, tmp_path):
 
 
 @pytest.mark.xfail(reason="written after this round's GPU budget was spent: not yet run on hardware", strict=False)
+@pytest.mark.timeout(600)
 def test_cli_restart_from_checkpoint_continues_bit_for_bit(K, tmp_path):
     """KAMINO_CHECKPOINT / KAMINO_RESTART (raw state checkpoint): frames 1-2 with a
     checkpoint, then a second process resuming for frames 3-4, must write the bytes an uninterrupted
@@ -669,6 +670,7 @@ def test_banded_step_is_bit_identical_to_single_gpu(K, nT, world):
 
 @pytest.mark.xfail(reason="written after this round's GPU budget was spent: the band-local solve has not run on hardware yet",
                    strict=False)
+@pytest.mark.timeout(180)
 @pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
 def test_banded_spike_mode_tracks_single_gpu(K, nT, world):
     """Reduced-interface (SPIKE) theta solve of the band-decomposed run (banded.SpikeInterface; band-local
