@@ -280,6 +280,14 @@ def main():
             ev1.record(stream)
             barrier()
         seconds = ev0.elapsed_time(ev1) * 1e-3
+        # the timed region is a few tens of milliseconds (one nvidia-smi sample): keep sampling the clocks
+        # over an untimed repetition of the same load for about a second and report both together
+        with ClockSampler(local_rank) as clocks_load:
+            t_load = time.perf_counter()
+            while time.perf_counter() - t_load < 1.0:
+                s.stepForward(DT, nSteps=K)
+                stream.synchronize()
+        clocks.samples.extend(clocks_load.samples)
 
         # ---- per-kernel CUDA-event times over K steps (same state, launched individually) ----
         nlaunch = int(lib.kamino_launches_per_step(s._ctx))
