@@ -288,6 +288,9 @@ def main():
                 s.stepForward(DT, nSteps=K)
                 stream.synchronize()
         clocks.samples.extend(clocks_load.samples)
+        upload_state()                      # thousands of extra steps later: back to the initial state
+        s.stepForward(DT, nSteps=W)
+        stream.synchronize()
 
         # ---- per-kernel CUDA-event times over K steps (same state, launched individually) ----
         nlaunch = int(lib.kamino_launches_per_step(s._ctx))
