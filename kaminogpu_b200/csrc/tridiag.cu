@@ -48,6 +48,12 @@ TriLaunch triLaunch(const GridParams& g, int batch)
     const int nT = g.nTheta, half = g.nPhi / 2;
     TriLaunch l;
     l.L = nT <= 64 ? 4 : nT <= 256 ? 8 : nT <= 1024 ? 16 : nT <= 4096 ? 32 : 64;
+    // experiment switch: KAMINO_TRI_L = chunk length (512 rows: 8 | 16 | 32; 2048 rows: 16 | 32 | 64)
+    if (const char* e = getenv("KAMINO_TRI_L")) {
+        const int want = atoi(e);
+        if ((nT == 512 && (want == 8 || want == 16 || want == 32)) || (nT == 2048 && (want == 16 || want == 32 || want == 64)))
+            l.L = want;
+    }
     l.P = nT / l.L;
     // W: as wide as possible (64-byte runs) while the grid still has about one block per SM and
     // the right-hand sides (nTheta * W float2) fit in shared memory (r01o A/B: W = 4 at 512 x 1024,
@@ -335,6 +341,8 @@ cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* sp
     KB_TRI_W(8, 16); KB_TRI_W(8, 32);                         // 128, 256
     KB_TRI_W(16, 32); KB_TRI_W(16, 64);                       // 512, 1024
     KB_TRI_W(32, 64);                                         // 2048
+    KB_TRI_W(8, 64); KB_TRI_W(32, 16);                        // 512 with KAMINO_TRI_L = 8 | 32
+    KB_TRI_W(16, 128); KB_TRI_W(64, 32);                      // 2048 with KAMINO_TRI_L = 16 | 64
     KB_TRI(2, 32, 128); KB_TRI(4, 32, 128); KB_TRI(8, 32, 128);   // 4096
     KB_TRI(2, 64, 128); KB_TRI(4, 64, 128);                   // 8192
 #undef KB_TRI_W
