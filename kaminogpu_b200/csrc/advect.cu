@@ -18,6 +18,12 @@ namespace { thread_local bool g_capturing = false; }
 
 void pdlSetCapturing(bool capturing) { g_capturing = capturing; }
 
+bool pdlTailEnabled()
+{
+    static const bool on = [] { const char* e = getenv("KAMINO_PDL_TAIL"); return e && atoi(e) != 0; }();
+    return on;
+}
+
 bool pdlEnabled()
 {
     static const bool on = [] { const char* e = getenv("KAMINO_PDL"); return e ? atoi(e) != 0 : true; }();
@@ -157,6 +163,7 @@ advectKernel(GridParams g, AdvectArgs a)
     const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
     const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
     const SamplerRegs sr(a.consts);            // read-only table: independent of the previous kernel
+    pdlTriggerTail(g);
     int block = blockIdx.x;
     bool isTile = block < a.tileBlocks;
     int particleBlock = block - a.tileBlocks;

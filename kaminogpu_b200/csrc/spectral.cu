@@ -151,6 +151,7 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
+    pdlTriggerTail(g);
     const int N = g.nPhi, half = N >> 1, log2T = g.log2NPhi - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
     const int pairs = (g.rowBegin + g.rowCount) >> 1;             // one past the last pair of the band
@@ -237,6 +238,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
+    pdlTriggerTail(g);
     const int N = g.nPhi, half = N >> 1, nT = g.nTheta, log2T = g.log2NPhi - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
     const int rowEnd = g.rowBegin + g.rowCount;

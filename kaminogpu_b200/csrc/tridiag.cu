@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(P * W)
 tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int pitch, int groupOffset)
 {
     extern __shared__ __align__(16) float2 sm[];
+    pdlTriggerTail(g);
     constexpr int nT = P * L;
     constexpr int kChunkPitch = L * W + W;              // float2 elements per chunk in smem
     constexpr int kThreads = P * W;
