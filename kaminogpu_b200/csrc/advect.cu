@@ -14,6 +14,11 @@
 
 namespace kb {
 
+// This file is compiled twice: as the product's advection (default) and, with -DKB_ADVECT_VARIANT
+// -DKB_TILE_STRIDE=64, as the padded-tile experiment build, which only contributes launchAdvectStride64.
+#ifdef KB_ADVECT_VARIANT
+#define launchAdvect launchAdvectStride64
+#else
 namespace { thread_local bool g_capturing = false; }
 
 void pdlSetCapturing(bool capturing) { g_capturing = capturing; }
@@ -29,6 +34,7 @@ bool pdlEnabled()
     static const bool on = [] { const char* e = getenv("KAMINO_PDL"); return e ? atoi(e) != 0 : true; }();
     return on && g_capturing;
 }
+#endif  // !KB_ADVECT_VARIANT
 
 namespace {
 
@@ -177,7 +183,7 @@ advectKernel(GridParams g, AdvectArgs a)
     pdlWait();
 
     if (isTile) {
-        __shared__ __align__(16) float tiles[3][kTileH * kTileW];
+        __shared__ __align__(16) float tiles[3][kTileH * kTileStride];
         const float* density = pinPointer(a.density + (size_t)sim * g.cells);
         const int log2TilesX = g.log2NPhi - 5;
         const int i0 = (block & ((1 << log2TilesX) - 1)) << 5;
@@ -197,7 +203,7 @@ advectKernel(GridParams g, AdvectArgs a)
             const int row = (f == 1) ? min(rowC, sr.nTheta - 2) : rowC;
             const float* src = (f == 0) ? velPhi : (f == 1) ? velTheta : density;
             const float4 v = __ldg(reinterpret_cast<const float4*>(src + (row * sr.N + col)));
-            *reinterpret_cast<float4*>(&tiles[f][r * kTileW + 4 * q]) = v;
+            *reinterpret_cast<float4*>(&tiles[f][r * kTileStride + 4 * q]) = v;
         }
         __syncthreads();
         unsigned tileBase = (unsigned)__cvta_generic_to_shared(&tiles[0][0]);
@@ -310,6 +316,7 @@ __global__ void locateKernel(const SamplerConsts* __restrict__ consts, long n, c
 
 } // namespace
 
+#ifndef KB_ADVECT_VARIANT
 void fillSamplerConsts(const GridParams& g, void* hostBlock64)
 {
     SamplerConsts c{};
@@ -328,9 +335,19 @@ void fillSamplerConsts(const GridParams& g, void* hostBlock64)
     static_assert(sizeof(SamplerConsts) == 64, "SamplerConsts is a 64-byte block");
     memcpy(hostBlock64, &c, sizeof(c));
 }
+#endif  // !KB_ADVECT_VARIANT
+
+#ifndef KB_ADVECT_VARIANT
+cudaError_t launchAdvectStride64(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);   // advect.cu, variant build
+#endif
 
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
 {
+#ifndef KB_ADVECT_VARIANT
+    // experiment switch: KAMINO_TILE_STRIDE=64 -> the padded-tile build of this file (sampler.cuh, kTileStride)
+    static const bool stride64 = [] { const char* e = getenv("KAMINO_TILE_STRIDE"); return e && atoi(e) == 64; }();
+    if (stride64) return launchAdvectStride64(g, a, batch, stream);
+#endif
     // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget). r01k A/B with the
     // branch-free interior path (C3 advect): 4 -> 217.6 us, 5 -> 209.1 us, 6 -> 198.6 us; equal at C2
     static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 6; }();
@@ -372,6 +389,7 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
     }
 }
 
+#ifndef KB_ADVECT_VARIANT
 cudaError_t launchAdvectParticles(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
 {
     if (!a.particles || g.numParticles <= 0) return cudaSuccess;
@@ -407,5 +425,7 @@ cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const fl
     }
     return cudaGetLastError();
 }
+
+#endif  // !KB_ADVECT_VARIANT
 
 } // namespace kb

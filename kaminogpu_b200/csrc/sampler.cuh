@@ -65,6 +65,9 @@ __device__ __forceinline__ Validated validateCoordInline(float phi, float theta)
 
 // Out of line (values in registers both ways): only lanes that cross a pole or the seam come
 // here, the callers test the in-range case first.
+#ifdef KB_ADVECT_VARIANT
+static          // the variant build of advect.cu is linked next to the default one
+#endif
 __device__ __noinline__ Validated validateCoord(float phi, float theta)
 {
     return validateCoordInline(phi, theta);
@@ -237,7 +240,16 @@ struct PendingSample { float v00, v01, v10, v11, alphaPhi, alphaTheta; };
 
 constexpr int kTileH = 13;      // 8 rows of cells + 2 above + 3 below
 constexpr int kTileW = 40;      // 32 columns + 4 left + 4 right
-constexpr int kTileBytes = kTileH * kTileW * 4;
+// Row stride of the tiles in shared memory (floats). 40 = dense. The experiment build of advect.cu
+// (-DKB_TILE_STRIDE=64, KAMINO_TILE_STRIDE=64 at run time) pads rows to 64: the bank of a cell is then
+// its column mod 32 whatever its row, so the lanes of a warp (distinct columns, one or two rows)
+// stop colliding (r01j ncu at C3: 27 % of the advection's shared-memory wavefronts are bank-conflict
+// replays with the dense layout, where rows are 8 banks apart).
+#ifndef KB_TILE_STRIDE
+#define KB_TILE_STRIDE 40
+#endif
+constexpr int kTileStride = KB_TILE_STRIDE;
+constexpr int kTileBytes = kTileH * kTileStride * 4;
 
 // The four corners of a cell from a shared-memory tile addressed by its 32-bit shared-window
 // address: explicit ld.shared with immediate offsets, so the tile base lives in one register for
@@ -247,9 +259,8 @@ __device__ __forceinline__ void loadTileCell(unsigned addr, PendingSample& p)
 {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p.v00) : "r"(addr));
     asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(p.v01) : "r"(addr));
-    asm volatile("ld.shared.f32 %0, [%1+160];" : "=f"(p.v10) : "r"(addr));
-    asm volatile("ld.shared.f32 %0, [%1+164];" : "=f"(p.v11) : "r"(addr));
-    static_assert(kTileW * 4 == 160, "immediate offsets above assume 40-column tiles");
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(p.v10) : "r"(addr), "n"(kTileStride * 4));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(p.v11) : "r"(addr), "n"(kTileStride * 4 + 4));
 }
 
 // Sample from the block's tile (tile blocks of the advection kernel). `tile` is the shared-window
@@ -291,7 +302,7 @@ __device__ __forceinline__ PendingSample sampleIssueTiled(const SamplerRegs& g, 
     if (ok) {
         p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
         p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
-        loadTileCell(tile + 4u * (unsigned)(tr * kTileW + tc), p);
+        loadTileCell(tile + 4u * (unsigned)(tr * kTileStride + tc), p);
     } else {
         const float v = sampleGeneral<KIND>(consts, field, phiRaw, thetaRaw);
         p.v00 = p.v01 = p.v10 = p.v11 = v;
@@ -320,8 +331,8 @@ __device__ __forceinline__ PendingSample sampleIssueFast(const SamplerRegs& g, f
     const int tr = thetaIndex - g.tileRow0;
     const int tc = phiIndex - g.tileCol0;
     bad = bad || (unsigned)tr >= (unsigned)(kTileH - 1) || (unsigned)tc >= (unsigned)(kTileW - 1);
-    // valid lanes: tr * kTileW + tc <= (kTileH - 2) * kTileW + kTileW - 2, never altered by the clamp
-    const unsigned cellIndex = min((unsigned)(tr * kTileW + tc), (unsigned)((kTileH - 2) * kTileW + kTileW - 2));
+    // valid lanes: tr * kTileStride + tc <= (kTileH - 2) * kTileStride + kTileW - 2, never altered by the clamp
+    const unsigned cellIndex = min((unsigned)(tr * kTileStride + tc), (unsigned)((kTileH - 2) * kTileStride + kTileW - 2));
     PendingSample p;
     p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
     p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
