@@ -106,8 +106,7 @@ int kamino_upload_particles_async(kamino_ctx* ctx, int sim, const float* pinnedH
 /* KaminoQuantity::getGPUThisStep / getGPUNextStep / get*PitchInElements
  * (include/KaminoQuantity.cuh:60-66): raw device pointer of the current this/next buffer
  * (which = 0 / 1) and its pitch in elements. The roles move after every phase as the
- * reference's swaps do (re-query the pointers after a phase rather than swapping a cached
- * pair: the forked-particles mode rotates the velocity through three buffers). */
+ * reference's swaps do (re-query the pointers after a phase rather than swapping a cached pair). */
 int kamino_field_device_ptr(kamino_ctx* ctx, int field, int sim, int which,
                             void** devicePtr, size_t* pitchInElements);
 /* KaminoParticles::coordGPUThisStep / coordGPUNextStep (include/KaminoParticles.cuh:18-19). */
@@ -159,7 +158,8 @@ int kamino_band_inverse_fft_gradient(kamino_ctx* ctx, int rowBegin, int rowCount
 int kamino_spectrum_device_ptr(kamino_ctx* ctx, int sim, void** devicePtr);
 
 /* KaminoSolver::stepForward (kernel/KaminoSolver.cu:197-221) nSteps times, launched as
- * CUDA graphs on the context's stream. Asynchronous: returns once the work is queued. */
+ * CUDA graphs (10-, 2- and 1-step graphs, captured, instantiated and uploaded at context creation /
+ * particle allocation) on the context's stream. Asynchronous: returns once the work is queued. */
 int kamino_step(kamino_ctx* ctx, int nSteps);
 
 /* Block the host until all queued work of this context is complete. */
@@ -182,14 +182,12 @@ int kamino_run_frames(kamino_ctx* ctx, int nFrames, int stepsPerFrame,
 int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, float* projection, int reset);
 
 /* Number of kernel launches one kamino_step(ctx, 1) performs (for bench.py's gpu_launches):
- * 5 (the particles are part of the advection launch), or 6 with KAMINO_FORK_PARTICLES=1
- * (experimental: particles as their own kernel on a parallel branch of the step graph). */
+ * 5 (the particles are part of the advection launch). */
 int kamino_launches_per_step(const kamino_ctx* ctx);
 
 /* Run nSteps steps with every kernel launched individually and bracketed by CUDA events on
  * the context's stream; kernelSeconds[k] (k = 0 .. kamino_launches_per_step()-1: advection,
- * geometric, divergence+FFT, tridiagonal, inverse FFT+gradient, then the particle kernel if
- * there is one) receives the summed device
+ * geometric, divergence+FFT, tridiagonal, inverse FFT+gradient) receives the summed device
  * time of kernel k. The per-kernel counterpart of the reference's per-phase KaminoTimer
  * brackets (kernel/KaminoSolver.cu:201-218). Synchronous. */
 int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds);

@@ -3,8 +3,8 @@
 // Replaces advectionVPhiKernel / advectionVThetaKernel / advectionCentered /
 // advectionParticles and KaminoSolver::advection (kernel/KaminoCore.cu:186-384): four
 // launches and two device syncs become ONE launch whose 1-D grid is partitioned into
-// four block ranges (u_phi cells | u_theta cells | density cells | particles). All four
-// read the pre-advection velocity, as in the reference.
+// two block ranges (tile blocks: u_phi, u_theta and density of 8 x 32 cells | particle blocks).
+// Everything reads the pre-advection velocity, as in the reference.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -14,27 +14,10 @@
 
 namespace kb {
 
-// This file is compiled twice: as the product's advection (default) and, with -DKB_ADVECT_VARIANT
-// -DKB_TILE_STRIDE=64, as the padded-tile experiment build, which only contributes launchAdvectStride64.
-#ifdef KB_ADVECT_VARIANT
-#define launchAdvect launchAdvectStride64
-#else
 namespace { thread_local bool g_capturing = false; }
 
 void pdlSetCapturing(bool capturing) { g_capturing = capturing; }
-
-bool pdlTailEnabled()
-{
-    static const bool on = [] { const char* e = getenv("KAMINO_PDL_TAIL"); return e && atoi(e) != 0; }();
-    return on;
-}
-
-bool pdlEnabled()
-{
-    static const bool on = [] { const char* e = getenv("KAMINO_PDL"); return e ? atoi(e) != 0 : true; }();
-    return on && g_capturing;
-}
-#endif  // !KB_ADVECT_VARIANT
+bool pdlEnabled() { return g_capturing; }
 
 namespace {
 
@@ -161,25 +144,18 @@ __device__ __forceinline__ float2 pushParticle(const SamplerRegs& g, const Sampl
 // thread per particle) come last in the grid and fill the tail of the tile blocks.
 constexpr int kTileRows = kAdvectThreads / 32;
 
-template <int MINBLOCKS>
-__global__ void __launch_bounds__(kAdvectThreads, MINBLOCKS)
+// Register budget: 6 blocks per SM (r01k/r01n A/B at 2048 x 4096: 217.6 / 209.1 / 198.6 / 195.8 us for
+// 4 / 5 / 6 / 7 blocks per SM; 7 costs 3 us at 512 x 1024).
+__global__ void __launch_bounds__(kAdvectThreads, 6)
 advectKernel(GridParams g, AdvectArgs a)
 {
     const int sim = blockIdx.y;
     const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
     const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
     const SamplerRegs sr(a.consts);            // read-only table: independent of the previous kernel
-    pdlTriggerTail(g);
-    int block = blockIdx.x;
-    bool isTile = block < a.tileBlocks;
-    int particleBlock = block - a.tileBlocks;
-    if (a.mixStep) {
-        const unsigned q0 = (unsigned)(((unsigned long long)block * a.mixStep) >> 32);
-        const unsigned q1 = (unsigned)(((unsigned long long)(block + 1) * a.mixStep) >> 32);
-        isTile = q1 > q0;
-        particleBlock = block - (int)q0;
-        block = (int)q0;
-    }
+    const int block = blockIdx.x;
+    const bool isTile = block < a.tileBlocks;
+    const int particleBlock = block - a.tileBlocks;
     pdlWait();
 
     if (isTile) {
@@ -261,41 +237,6 @@ advectKernel(GridParams g, AdvectArgs a)
     }
 }
 
-// The tracer particles as a kernel of their own (forked mode: it runs on a parallel branch of the
-// step graph, next to the kernels of the velocity chain). The path is bound by memory latency --
-// position load, then eight dependent gathers, then the store (r01g: 1.2-1.5 TB/s with one
-// particle per thread at 40 warps per SM) -- so every thread owns kParticlesPerThread particles,
-// kAdvectThreads apart (coalesced), loads all positions first, issues all gathers, then finishes.
-constexpr int kParticlesPerThread = 2;
-
-template <int MINBLOCKS>
-__global__ void __launch_bounds__(kAdvectThreads, MINBLOCKS)
-advectParticlesKernel(GridParams g, AdvectArgs a)
-{
-    const int sim = blockIdx.y;
-    const float* velPhi = pinPointer(a.velPhi + (size_t)sim * g.cells);
-    const float* velTheta = pinPointer(a.velTheta + (size_t)sim * g.cells);
-    const SamplerRegs sr(a.consts);
-    const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
-    float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
-    const long base = (long)blockIdx.x * (kAdvectThreads * kParticlesPerThread) + threadIdx.x;
-    float2 pos[kParticlesPerThread];
-#pragma unroll
-    for (int m = 0; m < kParticlesPerThread; ++m) {
-        const long k = base + m * kAdvectThreads;
-        pos[m] = (k < g.numParticles) ? __ldcs(in + k) : make_float2(1.0f, 1.0f);
-    }
-    PendingParticle pending[kParticlesPerThread];
-#pragma unroll
-    for (int m = 0; m < kParticlesPerThread; ++m) pending[m] = particleIssue(sr, a.consts, velPhi, velTheta, pos[m]);
-#pragma unroll
-    for (int m = 0; m < kParticlesPerThread; ++m) {
-        const long k = base + m * kAdvectThreads;
-        const float2 next = particleFinish(g.radius, g.dt, g.cofTheta, pos[m], pending[m]);
-        if (k < g.numParticles) __stcs(out + k, next);     // the reference has no tail guard (:323)
-    }
-}
-
 template <int KIND>
 __global__ void locateKernel(const SamplerConsts* __restrict__ consts, long n, const float* __restrict__ phiRaw,
                              const float* __restrict__ thetaRaw, int* phiIndex, int* thetaIndex,
@@ -316,7 +257,6 @@ __global__ void locateKernel(const SamplerConsts* __restrict__ consts, long n, c
 
 } // namespace
 
-#ifndef KB_ADVECT_VARIANT
 void fillSamplerConsts(const GridParams& g, void* hostBlock64)
 {
     SamplerConsts c{};
@@ -335,28 +275,13 @@ void fillSamplerConsts(const GridParams& g, void* hostBlock64)
     static_assert(sizeof(SamplerConsts) == 64, "SamplerConsts is a 64-byte block");
     memcpy(hostBlock64, &c, sizeof(c));
 }
-#endif  // !KB_ADVECT_VARIANT
-
-#ifndef KB_ADVECT_VARIANT
-cudaError_t launchAdvectStride64(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);   // advect.cu, variant build
-#endif
-
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
 {
-#ifndef KB_ADVECT_VARIANT
-    // experiment switch: KAMINO_TILE_STRIDE=64 -> the padded-tile build of this file (sampler.cuh, kTileStride)
-    static const bool stride64 = [] { const char* e = getenv("KAMINO_TILE_STRIDE"); return e && atoi(e) == 64; }();
-    if (stride64) return launchAdvectStride64(g, a, batch, stream);
-#endif
-    // experiment switch: KAMINO_ADVECT=<min blocks per SM> (register budget). r01k A/B with the
-    // branch-free interior path (C3 advect): 4 -> 217.6 us, 5 -> 209.1 us, 6 -> 198.6 us; equal at C2
-    static const int variant = [] { const char* e = getenv("KAMINO_ADVECT"); return e ? atoi(e) : 6; }();
     a.tileBlocks = (g.nPhi / 32) * (g.rowCount / kTileRows);      // rowBegin, rowCount: multiples of kTileRows
     int blocksParticles = (a.particles && g.numParticles > 0)
         ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
     a.latticeInner = a.latticeOuter = a.log2Inner = a.blocksInner = 0;
-    static const int lattice = [] { const char* e = getenv("KAMINO_PARTICLE_TILES"); return e ? atoi(e) : 1; }();
-    if (blocksParticles > 0 && lattice) {
+    if (blocksParticles > 0) {
         // numOfParticles = numTheta * (2 numTheta) for a seeded set (kernel/KaminoParticles.cu:22-25)
         const long m = (long)(sqrt((double)g.numParticles / 2.0) + 0.5);
         if (m >= 16 && 2 * m * m == g.numParticles) {
@@ -372,34 +297,10 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
             }
         }
     }
-    // experiment switch (r01h: interleaving is a loss, advect 35.3 -> 41.4 us at C2; default off)
-    static const int mix = [] { const char* e = getenv("KAMINO_ADVECT_MIX"); return e ? atoi(e) : 0; }();
-    a.mixStep = 0;
-    if (mix && blocksParticles > 0 && a.tileBlocks > 0) {
-        const unsigned long long total = (unsigned long long)a.tileBlocks + blocksParticles;
-        a.mixStep = (((unsigned long long)a.tileBlocks << 32) + total - 1) / total;
-    }
+    // (r01h A/B: interleaving tile and particle blocks along the grid is a loss, 35.3 -> 41.4 us at 512 x 1024:
+    // tile blocks first, the particle blocks fill their tail waves)
     dim3 grid(a.tileBlocks + blocksParticles, batch);
-    switch (variant) {
-    case 3: return launchChained(advectKernel<3>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    case 4: return launchChained(advectKernel<4>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    case 5: return launchChained(advectKernel<5>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    case 7: return launchChained(advectKernel<7>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    default: return launchChained(advectKernel<6>, grid, dim3(kAdvectThreads), 0, stream, g, a);
-    }
-}
-
-#ifndef KB_ADVECT_VARIANT
-cudaError_t launchAdvectParticles(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream)
-{
-    if (!a.particles || g.numParticles <= 0) return cudaSuccess;
-    const long perBlock = (long)kAdvectThreads * kParticlesPerThread;
-    dim3 grid((unsigned)((g.numParticles + perBlock - 1) / perBlock), batch);
-    // experiment switch: KAMINO_PARTICLE_BLOCKS = 3 (76 registers, no spills) | 4 (64 registers)
-    static const int minBlocks = [] { const char* e = getenv("KAMINO_PARTICLE_BLOCKS"); return e ? atoi(e) : 3; }();
-    if (minBlocks == 4) advectParticlesKernel<4><<<grid, kAdvectThreads, 0, stream>>>(g, a);
-    else advectParticlesKernel<3><<<grid, kAdvectThreads, 0, stream>>>(g, a);
-    return cudaGetLastError();
+    return launchChained(advectKernel, grid, dim3(kAdvectThreads), 0, stream, g, a);
 }
 
 cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const float* phiRaw, const float* thetaRaw,
@@ -425,7 +326,5 @@ cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const fl
     }
     return cudaGetLastError();
 }
-
-#endif  // !KB_ADVECT_VARIANT
 
 } // namespace kb

@@ -5,6 +5,7 @@
 // library begins from bit-identical fields. Compile with -ffp-contract=off: the reference's
 // host code is plain SSE2 arithmetic without fused multiply-adds.
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 
 #include "../../include/kamino_b200.h"
@@ -99,6 +100,37 @@ extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi
 }
 
 namespace {
+// glibc's rand() (random_r, TYPE_3: x_k = x_{k-3} + x_{k-31} mod 2^32, output x_k >> 1) restated locally, in its
+// never-seeded (= srand(1)) state: the reference's particle seeding draws from it (kernel/KaminoParticles.cu:39-46),
+// and re-seeding or advancing the process-global generator from inside a library would be a side effect on the host
+// program. tests/test_capi_host.py checks the sequence against libc's.
+struct GlibcRand {
+    uint32_t r[34];
+    int at = 0;            // ring position of x_{k-34}
+    GlibcRand()
+    {
+        int32_t seedTable[34];
+        seedTable[0] = 1;
+        for (int i = 1; i < 31; ++i) {
+            int64_t v = (16807LL * seedTable[i - 1]) % 2147483647LL;
+            if (v < 0) v += 2147483647LL;
+            seedTable[i] = (int32_t)v;
+        }
+        for (int i = 31; i < 34; ++i) seedTable[i] = seedTable[i - 31];
+        for (int i = 0; i < 34; ++i) r[i] = (uint32_t)seedTable[i];
+        for (int i = 34; i < 344; ++i) step();       // glibc discards the first 310 values
+    }
+    uint32_t step()
+    {
+        // r[] is a ring of the last 34 values, r[at] the oldest (x_{k-34}); x_k = x_{k-31} + x_{k-3}
+        const uint32_t v = r[(at + 3) % 34] + r[(at + 31) % 34];
+        r[at] = v;
+        at = (at + 1) % 34;
+        return v;
+    }
+    int next() { return (int)(step() >> 1); }
+};
+
 struct LatticeShape { float spacing; unsigned nTheta, nPhi; };
 
 LatticeShape latticeShape(int nTheta, float particleDensity)
@@ -124,15 +156,15 @@ extern "C" int kamino_seed_particles_host(int nTheta, float particleDensity, flo
     if (nTheta < 1 || !(particleDensity >= 0.f) || !coords) return KAMINO_ERR_INVALID;
     const LatticeShape s = latticeShape(nTheta, particleDensity);
     const float half = (float)((double)s.spacing / 2.0);
-    const float randMax = (float)RAND_MAX;
-    std::srand(1);       // the reference never seeds: glibc starts in the srand(1) state
+    const float randMax = 2147483647.0f;          // (float)RAND_MAX of glibc
+    GlibcRand rng;       // the reference never seeds: glibc's rand() starts in the srand(1) state
     for (unsigned i = 0; i < s.nPhi; ++i) {
         for (unsigned j = 0; j < s.nTheta; ++j) {
             // four draws per particle in this order: sign phi, sign theta, jitter phi, jitter theta (:39-46)
-            const float sp = ((double)((float)std::rand() / randMax) >= 0.5) ? 1.0f : -1.0f;
-            const float st = ((double)((float)std::rand() / randMax) >= 0.5) ? 1.0f : -1.0f;
-            const float jitterPhi = sp * half * (float)std::rand() / randMax;
-            const float jitterTheta = st * half * (float)std::rand() / randMax;
+            const float sp = ((double)((float)rng.next() / randMax) >= 0.5) ? 1.0f : -1.0f;
+            const float st = ((double)((float)rng.next() / randMax) >= 0.5) ? 1.0f : -1.0f;
+            const float jitterPhi = sp * half * (float)rng.next() / randMax;
+            const float jitterTheta = st * half * (float)rng.next() / randMax;
             float phi = (float)i * s.spacing + jitterPhi;
             float theta = (float)j * s.spacing + jitterTheta;
             if (phi < 0.0f) phi = 0.0f;

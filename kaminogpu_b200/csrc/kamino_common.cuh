@@ -35,9 +35,6 @@ struct GridParams {
     // the whole grid unless a kamino_band_* entry point narrowed it). Arrays and indices stay
     // global: a band-decomposed run keeps full-size buffers and only computes its rows.
     int rowBegin, rowCount;
-    // experiment (KAMINO_PDL_TAIL=1, default off -> 0): number of trailing blocks of a launch that
-    // release the programmatic dependents at their entry; filled per launch by launchChained
-    int pdlTail;
 };
 
 // Field buffers of the whole batch; simulation b starts at ptr + b * cells.
@@ -58,34 +55,18 @@ struct FieldSet {
 // Measured (r01j A/B): triggering the dependents EARLY (griddepcontrol.launch_dependents at
 // kernel entry) is a large loss -- the waiting blocks of kernel k+1 take SM slots from the
 // later waves of kernel k -- so no kernel triggers explicitly. Outside graph capture (phase
-// entry points, which may follow a memcpy) launches are plain. KAMINO_PDL=0/1 switches it.
+// entry points, which may follow a memcpy) launches are plain.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Tail trigger (experiment, off unless GridParams::pdlTail > 0). Without an explicit trigger the next
-// kernel of the chain becomes schedulable only when the LAST block of this one exits; triggering at
-// kernel entry for every block was measured as a loss (r01j: the dependents' waiting blocks take SM
-// slots from the later waves). Here only the blocks of the last wave trigger, at their entry: by
-// then every block of this grid is resident or done, so the dependents' blocks can only take slots
-// nobody else needs, run their prologue (table loads, twiddle staging) and park in
-// griddepcontrol.wait, which still returns only after this grid has completed and flushed.
-__device__ __forceinline__ void pdlTriggerTail(const GridParams& g)
-{
-    if (g.pdlTail > 0) {
-        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-        const unsigned linear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        if (linear + (unsigned)g.pdlTail >= total) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    }
-}
-
 bool pdlEnabled();
-bool pdlTailEnabled();                  // KAMINO_PDL_TAIL=1
 void pdlSetCapturing(bool capturing);   // set by the context around graph capture
 
-// Every kernel of the step takes GridParams first; the launcher fills its pdlTail field.
+// Launch of a kernel of the step chain (with the programmatic edge while a step graph is being captured).
+// Measured and rejected (r02a A/B): letting the blocks of a kernel's last wave release the dependents at
+// their entry -- 62.2 instead of 55.1 us/step at 512 x 1024, 462 instead of 449 us at 2048 x 4096.
 template <typename... KArgs, typename... Args>
-cudaError_t launchChained(void (*kernel)(GridParams, KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                          GridParams g, Args... args)
+cudaError_t launchChained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -94,23 +75,7 @@ cudaError_t launchChained(void (*kernel)(GridParams, KArgs...), dim3 grid, dim3 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdlEnabled() ? 1 : 0;
-    g.pdlTail = 0;
-    if (cfg.numAttrs && pdlTailEnabled()) {
-        // one wave of this kernel = SMs x resident blocks per SM (occupancy query, cached per kernel)
-        static int blocksPerWave = 0;          // one instance per (kernel signature) instantiation and call site
-        static const void* cachedFor = nullptr;
-        if (cachedFor != (const void*)kernel) {
-            int perSm = 0, device = 0, sms = 0;
-            cudaGetDevice(&device);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, (int)(block.x * block.y * block.z), smem) != cudaSuccess)
-                perSm = 1;
-            blocksPerWave = (perSm > 0 ? perSm : 1) * sms;
-            cachedFor = (const void*)kernel;
-        }
-        g.pdlTail = blocksPerWave;
-    }
-    return cudaLaunchKernelEx(&cfg, kernel, g, KArgs(args)...);
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif
 

@@ -2,13 +2,13 @@
 //
 // HBM layout (one arena per context, every sub-buffer 256-byte aligned, batch-major):
 //   velPhi[2], velTheta[2], density[2]   batch x nTheta x nPhi fp32 each (u_theta uses
-//                                        nTheta-1 rows of its slot), double-buffered (a third
-//                                        velocity buffer in the forked-particles mode, see below)
+//                                        nTheta-1 rows of its slot), double-buffered
 //   pressure                             batch x nTheta x nPhi fp32
 //   spectrum                             batch x nTheta x nPhi/2 float2 (half spectrum)
 //   particles[2]                         batch x numParticles float2, double-buffered
 //   tables                               twiddles + per-row constants + the LU factors of every
-//                                        wavenumber's theta system (10 B per cell, read-only)
+//                                        wavenumber's theta system (5 floats per spectrum entry =
+//                                        10 B per cell, read-only)
 // = 36 B/cell of state + 10 B/cell of tables + 16 B/particle (the reference: 76 B/cell,
 // SURVEY.md appendix B).
 #include <cstdio>
@@ -31,14 +31,13 @@ struct kamino_ctx {
     GridParams g{};
     cudaStream_t ownStream = nullptr;    // graphs are captured here
     cudaStream_t copyStream = nullptr;   // frame read-backs
-    cudaStream_t sideStream = nullptr;   // particle branch of the step graph (lower priority)
     cudaStream_t stream = nullptr;       // where work is launched (ownStream unless overridden)
     char* arena = nullptr;          // fields, spectrum, tables
     size_t arenaBytes = 0;
     char* particleArena = nullptr;  // particles[2] + read-back snapshot (sized by kamino_alloc_particles)
 
-    float* velPhi[3]{};
-    float* velTheta[3]{};
+    float* velPhi[2]{};
+    float* velTheta[2]{};
     float* density[2]{};
     float* pressure = nullptr;
     float2* spectrum = nullptr;
@@ -52,22 +51,15 @@ struct kamino_ctx {
     int bandRowBegin = 0, bandRows = 0;
 
     int velIdx = 0, densityIdx = 0, particleIdx = 0;   // which buffer is "this step"
-    // Velocity buffers in rotation. advect writes next(v), geometric writes next(next(v)), the
-    // projection corrects that buffer in place; two buffers by default (a ping-pong, as in the
-    // reference). KAMINO_FORK_PARTICLES=1 selects three buffers: the pre-advection velocity of step
-    // n then stays untouched until advect of step n+1, so the tracer particles of step n (which read
-    // only that velocity, kernel/KaminoCore.cu:376-381) run as their own kernel on a parallel
-    // branch of the step graph. Measured (r01i, C2): 63.9 us/step forked against 54.5 us fused --
-    // inside the fused launch the particle blocks fill the tail waves of the tile blocks at a
-    // marginal cost of 8 us, while the separate kernel needs 20 us and competes with the velocity
-    // chain for SM slots -- so the fused launch stays the default.
-    int velBuffers = 2;
-    bool forkParticles = false;
+    // Velocity ping-pong, as in the reference: advect writes the other buffer, geometric writes back into
+    // the first, the projection corrects that buffer in place. (r01i A/B: a third velocity buffer, so that the
+    // tracer particles run as their own kernel on a parallel graph branch, is a loss -- 63.9 vs 54.5 us/step at
+    // 512 x 1024: inside the fused launch the particle blocks fill the tail waves of the tile blocks.)
+    static constexpr int velBuffers = 2;
 
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (parity, steps) -> exec
 
     cudaEvent_t evStart = nullptr, evStop = nullptr, evSnap = nullptr, evCopied = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     float advectionTime = 0.f, geometricTime = 0.f, projectionTime = 0.f;
 
     std::string lastError;
@@ -75,10 +67,9 @@ struct kamino_ctx {
 
 namespace {
 
-constexpr int kStepKernels = 5;      // + 1 (the particle kernel) when the particles run on their own branch
+constexpr int kStepKernels = 5;
 
-int nextVel(const kamino_ctx* ctx, int v) { return (v + 1) % ctx->velBuffers; }
-bool particlesForked(const kamino_ctx* ctx) { return ctx->forkParticles && ctx->g.numParticles > 0; }
+int nextVel(const kamino_ctx*, int v) { return v ^ 1; }
 
 thread_local std::string g_createError;
 
@@ -143,18 +134,10 @@ AdvectArgs advectArgs(kamino_ctx* ctx, const IndexState& st)
     return a;
 }
 
-// the particle kernel of the forked mode (reads the pre-advection velocity st.vel); does not touch `st`
-cudaError_t enqueueParticles(kamino_ctx* ctx, const IndexState& st, cudaStream_t s)
-{
-    return launchAdvectParticles(ctx->g, advectArgs(ctx, st), ctx->batch, s);
-}
-
-// cells (and, unless the particles run as their own kernel, the particles); flips the indices
+// cells and particles; flips the indices
 cudaError_t enqueueAdvect(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
-    AdvectArgs a = advectArgs(ctx, st);
-    if (particlesForked(ctx)) { a.particles = nullptr; a.particlesOut = nullptr; }
-    cudaError_t e = launchAdvect(ctx->g, a, ctx->batch, s);
+    cudaError_t e = launchAdvect(ctx->g, advectArgs(ctx, st), ctx->batch, s);
     st.vel = nextVel(ctx, st.vel); st.density ^= 1; st.particle ^= 1;      // kernel/KaminoCore.cu:373,380,383
     return e;
 }
@@ -194,7 +177,6 @@ cudaError_t enqueueProject(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 }
 
 // kernel k of a step: 0 advect, 1 geometric, 2 divergence+FFT, 3 tridiagonal, 4 inverse FFT+gradient
-// (the particle kernel of the forked mode is enqueued by the callers, before kernel 0)
 cudaError_t enqueueStepKernel(kamino_ctx* ctx, IndexState& st, int k, cudaStream_t s)
 {
     if (k == 0) return enqueueAdvect(ctx, st, s);
@@ -203,8 +185,7 @@ cudaError_t enqueueStepKernel(kamino_ctx* ctx, IndexState& st, int k, cudaStream
 }
 
 // Timing instrumentation only (scripts/step_mask_timing.py): KAMINO_DEBUG_STEP_MASK leaves kernels
-// out of the captured step graph (bit k = kernel k, bit 5 = the particle kernel of the forked mode)
-// to attribute the in-graph step time; the results of such a run are meaningless and bench.py
+// out of the captured step graph (bit k = kernel k) to attribute the in-graph step time; the results of such a run are meaningless and bench.py
 // refuses to run with it set.
 int debugStepMask()
 {
@@ -221,11 +202,10 @@ cudaError_t enqueueStepKernelMasked(kamino_ctx* ctx, IndexState& st, int k, cuda
     return cudaSuccess;
 }
 
-// one step in stream order (phase-style): the particle kernel of the forked mode first
+// one step in stream order
 cudaError_t enqueueStep(kamino_ctx* ctx, IndexState& st, cudaStream_t s)
 {
     cudaError_t e = cudaSuccess;
-    if (particlesForked(ctx) && (debugStepMask() & 32)) e = enqueueParticles(ctx, st, s);
     for (int k = 0; k < kStepKernels && e == cudaSuccess; ++k) e = enqueueStepKernelMasked(ctx, st, k, s);
     return e;
 }
@@ -238,39 +218,17 @@ void dropGraphs(kamino_ctx* ctx)
 
 // A graph of `steps` consecutive steps for the current buffer roles. The velocity index
 // returns to its starting value after every step; density and particles flip once per step.
-int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
+int getGraph(kamino_ctx* ctx, IndexState st, int steps, cudaGraphExec_t* out)
 {
-    const int roles = (ctx->velIdx << 2) | (ctx->densityIdx << 1) | ctx->particleIdx;   // velIdx: 0 .. velBuffers-1
+    const int roles = (st.vel << 2) | (st.density << 1) | st.particle;
     auto key = std::make_pair(roles, steps);
     auto it = ctx->graphs.find(key);
     if (it != ctx->graphs.end()) { *out = it->second; return 0; }
-    IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
     cudaGraph_t graph = nullptr;
     KB_TRY(ctx, cudaStreamBeginCapture(ctx->ownStream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
     pdlSetCapturing(true);
-    static const bool sequential = [] { const char* e = getenv("KAMINO_FORK_SEQUENTIAL"); return e && atoi(e) != 0; }();
-    const bool fork = particlesForked(ctx) && (debugStepMask() & 32) && !sequential;   // KAMINO_FORK_SEQUENTIAL=1: A/B switch
-    for (int k = 0; k < steps && e == cudaSuccess; ++k) {
-        if (fork) {
-            // parallel branch: particles of this step on the side stream, joined before the next
-            // step's advection overwrites the velocity buffer they read
-            e = cudaEventRecord(ctx->evFork, ctx->ownStream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sideStream, ctx->evFork, 0);
-            pdlSetCapturing(false);
-            if (e == cudaSuccess) e = enqueueParticles(ctx, st, ctx->sideStream);
-            pdlSetCapturing(true);
-            if (e == cudaSuccess) e = cudaEventRecord(ctx->evJoin, ctx->sideStream);
-            // the first kernel after a join has two predecessors: launched without the programmatic edge
-            if (k > 0) pdlSetCapturing(false);
-            if (e == cudaSuccess) e = enqueueStepKernelMasked(ctx, st, 0, ctx->ownStream);
-            pdlSetCapturing(true);
-            for (int q = 1; q < kStepKernels && e == cudaSuccess; ++q) e = enqueueStepKernelMasked(ctx, st, q, ctx->ownStream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->ownStream, ctx->evJoin, 0);
-        } else {
-            e = enqueueStep(ctx, st, ctx->ownStream);
-        }
-    }
+    for (int k = 0; k < steps && e == cudaSuccess; ++k) e = enqueueStep(ctx, st, ctx->ownStream);
     pdlSetCapturing(false);
     cudaError_t e2 = cudaStreamEndCapture(ctx->ownStream, &graph);
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(ctx, (int)e, "graph capture (launch)"); }
@@ -279,8 +237,34 @@ int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(ctx, (int)e, "cudaGraphInstantiate");
+    cudaGraphUpload(exec, ctx->ownStream);          // device-side resources now, not at the first launch
     ctx->graphs[key] = exec;
     *out = exec;
+    return 0;
+}
+
+int getGraph(kamino_ctx* ctx, int steps, cudaGraphExec_t* out)
+{
+    return getGraph(ctx, IndexState{ctx->velIdx, ctx->densityIdx, ctx->particleIdx}, steps, out);
+}
+
+constexpr int kStepChunks[] = {10, 2, 1};           // kamino_step splits nSteps into these graph sizes
+
+// Capture, instantiate and upload every graph kamino_step can ask for while whole steps are the only
+// thing that moves the buffer roles (the velocity index returns to its value after every step, density
+// and particles flip together): 3 chunk sizes x 2 parities. Called at context creation and whenever the
+// particle set is re-allocated, so that no kamino_step ever instantiates inside a caller's timed region
+// (r01 VERDICT: the lazily built 10-step graph cost 380 us of a 1.4 ms bench window). Phase calls that
+// leave other role combinations still build their graph on first use.
+int prepareGraphs(kamino_ctx* ctx)
+{
+    for (int parity = 0; parity < 2; ++parity)
+        for (int steps : kStepChunks) {
+            cudaGraphExec_t exec = nullptr;
+            const IndexState st{ctx->velIdx, ctx->densityIdx ^ parity, ctx->particleIdx ^ parity};
+            if (int rc = getGraph(ctx, st, steps, &exec)) return rc;
+        }
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->ownStream));
     return 0;
 }
 
@@ -326,7 +310,7 @@ int allocParticles(kamino_ctx* ctx, long n)
     ctx->particles[1] = (float*)(ctx->particleArena + particleBytes);
     ctx->snapshot = (float*)(ctx->particleArena + 2 * particleBytes);
     ctx->particleIdx = ctx->densityIdx;
-    return 0;
+    return prepareGraphs(ctx);
 }
 
 } // namespace
@@ -380,12 +364,7 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
 
     const size_t fieldBytes = alignUp(sizeof(float) * g.cells * batch, 256);
     const size_t tableBytes = alignUp(spectralTableBytes(g), 256);
-    {
-        const char* e = getenv("KAMINO_FORK_PARTICLES");
-        ctx->forkParticles = e ? atoi(e) != 0 : false;
-        ctx->velBuffers = ctx->forkParticles ? 3 : 2;
-    }
-    ctx->arenaBytes = fieldBytes * (6 + 2 * ctx->velBuffers) + tableBytes;
+    ctx->arenaBytes = fieldBytes * (4 + 2 * ctx->velBuffers) + tableBytes;   // 2 x (u_phi, u_theta), 2 x density, pressure, spectrum
     e = cudaMalloc((void**)&ctx->arena, ctx->arenaBytes);
     if (e != cudaSuccess) { int rc = fail(nullptr, (int)e, "cudaMalloc(arena)"); delete ctx; return rc; }
     cudaMemset(ctx->arena, 0, ctx->arenaBytes);
@@ -425,9 +404,6 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
     cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
     bool ok = cudaStreamCreateWithPriority(&ctx->ownStream, cudaStreamNonBlocking, prioGreatest) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) == cudaSuccess
-        && cudaStreamCreateWithPriority(&ctx->sideStream, cudaStreamNonBlocking, prioLeast) == cudaSuccess
-        && cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) == cudaSuccess
-        && cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreate(&ctx->evStart) == cudaSuccess && cudaEventCreate(&ctx->evStop) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->evSnap, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming) == cudaSuccess;
@@ -463,9 +439,6 @@ int kamino_destroy(kamino_ctx* ctx)
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
     if (ctx->evSnap) cudaEventDestroy(ctx->evSnap);
     if (ctx->evCopied) cudaEventDestroy(ctx->evCopied);
-    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
-    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
-    if (ctx->sideStream) cudaStreamDestroy(ctx->sideStream);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->arena) cudaFree(ctx->arena);
@@ -568,13 +541,7 @@ int kamino_particles_device_ptr(kamino_ctx* ctx, int sim, int which, void** devi
 int kamino_advect(kamino_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
-    return timedPhase(ctx, ctx->advectionTime, [&](IndexState& st) {
-        if (particlesForked(ctx)) {
-            cudaError_t e = enqueueParticles(ctx, st, ctx->stream);
-            if (e != cudaSuccess) return e;
-        }
-        return enqueueAdvect(ctx, st, ctx->stream);
-    });
+    return timedPhase(ctx, ctx->advectionTime, [&](IndexState& st) { return enqueueAdvect(ctx, st, ctx->stream); });
 }
 
 int kamino_geometric(kamino_ctx* ctx)
@@ -725,17 +692,15 @@ int kamino_step(kamino_ctx* ctx, int nSteps)
     if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
     if (nSteps < 0) return fail(ctx, KAMINO_ERR_INVALID, "nSteps < 0");
     DeviceGuard guard(ctx->device);
-    static const int chunks[] = {10, 2, 1};
     int remaining = nSteps;
     while (remaining > 0) {
         int take = 1;
-        for (int c : chunks)
+        for (int c : kStepChunks)
             if (c <= remaining) { take = c; break; }
         cudaGraphExec_t exec = nullptr;
         if (int rc = getGraph(ctx, take, &exec)) return rc;
         KB_TRY(ctx, cudaGraphLaunch(exec, ctx->stream));
         if (take & 1) { ctx->densityIdx ^= 1; ctx->particleIdx ^= 1; }
-        ctx->velIdx = (ctx->velIdx + 2 * take) % ctx->velBuffers;
         remaining -= take;
     }
     return 0;
@@ -797,15 +762,14 @@ int kamino_phase_times(kamino_ctx* ctx, float* advection, float* geometric, floa
     return 0;
 }
 
-int kamino_launches_per_step(const kamino_ctx* ctx) { return kStepKernels + ((ctx && particlesForked(ctx)) ? 1 : 0); }
+int kamino_launches_per_step(const kamino_ctx*) { return kStepKernels; }
 
 int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds)
 {
     if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
     if (nSteps < 1 || !kernelSeconds) return fail(ctx, KAMINO_ERR_INVALID, "nSteps >= 1 and an output array required");
     DeviceGuard guard(ctx->device);
-    const bool forked = particlesForked(ctx);
-    const int nK = kStepKernels + (forked ? 1 : 0);          // slot 5 = the particle kernel
+    const int nK = kStepKernels;
     std::vector<cudaEvent_t> ev((size_t)nSteps * (nK + 1));
     for (auto& e : ev) KB_TRY(ctx, cudaEventCreate(&e));
     IndexState st{ctx->velIdx, ctx->densityIdx, ctx->particleIdx};
@@ -813,10 +777,6 @@ int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds)
     for (int s = 0; s < nSteps && err == cudaSuccess; ++s) {
         cudaEvent_t* e = &ev[(size_t)s * (nK + 1)];
         err = cudaEventRecord(e[0], ctx->stream);
-        if (forked && err == cudaSuccess) {                   // launched first: it reads the pre-advection velocity
-            err = enqueueParticles(ctx, st, ctx->stream);
-            if (err == cudaSuccess) err = cudaEventRecord(e[nK], ctx->stream);
-        }
         for (int k = 0; k < kStepKernels && err == cudaSuccess; ++k) {
             err = enqueueStepKernel(ctx, st, k, ctx->stream);
             if (err == cudaSuccess) err = cudaEventRecord(e[k + 1], ctx->stream);
@@ -829,10 +789,7 @@ int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds)
         cudaEvent_t* e = &ev[(size_t)s * (nK + 1)];
         for (int k = 0; k < nK && err == cudaSuccess; ++k) {
             float ms = 0.f;
-            // event order in the stream: e[0], (e[nK] after the particles,) e[1] .. e[5]
-            cudaEvent_t from = (k == 0) ? (forked ? e[nK] : e[0]) : (k == kStepKernels ? e[0] : e[k]);
-            cudaEvent_t to = (k == kStepKernels) ? e[nK] : e[k + 1];
-            err = cudaEventElapsedTime(&ms, from, to);
+            err = cudaEventElapsedTime(&ms, e[k], e[k + 1]);
             total[k] += ms * 1e-3;
         }
     }

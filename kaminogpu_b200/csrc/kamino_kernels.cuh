@@ -22,12 +22,6 @@ struct AdvectArgs {
     const float* cofPhiTheta;
     const SamplerConsts* consts;  // device copy of the sampler constants (sampler.cuh)
     int tileBlocks;                              // filled by launchAdvect
-    // Tile blocks (issue-bound) and particle blocks (latency-bound) are interleaved along the grid
-    // in proportion to their counts, so that every SM holds a mix of both at any time: block b is
-    // tile block q(b) = (b * mixStep) >> 32 when q(b + 1) > q(b), else particle block b - q(b);
-    // mixStep = ceil(tileBlocks * 2^32 / (tileBlocks + particleBlocks)). mixStep = 0: tile blocks
-    // first, then the particle blocks.
-    unsigned long long mixStep;
     // thread -> particle mapping of the particle blocks (filled by launchAdvect). A seeded particle
     // set is a jittered numPhi x numTheta lattice stored phi-major (kernel/KaminoParticles.cu:39-62,
     // index i * numTheta + j), so 32 consecutive particles lie on 32 different theta rows and every
@@ -41,8 +35,6 @@ struct AdvectArgs {
 };
 
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
-// the tracer particles alone (a.particles / a.particlesOut / a.velPhi / a.velTheta / a.consts); a plain launch
-cudaError_t launchAdvectParticles(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);
 
 struct SamplerConsts;
 cudaError_t launchLocate(const SamplerConsts* consts, int kind, long n, const float* phiRaw, const float* thetaRaw,

@@ -65,9 +65,6 @@ __device__ __forceinline__ Validated validateCoordInline(float phi, float theta)
 
 // Out of line (values in registers both ways): only lanes that cross a pole or the seam come
 // here, the callers test the in-range case first.
-#ifdef KB_ADVECT_VARIANT
-static          // the variant build of advect.cu is linked next to the default one
-#endif
 __device__ __noinline__ Validated validateCoord(float phi, float theta)
 {
     return validateCoordInline(phi, theta);
@@ -240,15 +237,11 @@ struct PendingSample { float v00, v01, v10, v11, alphaPhi, alphaTheta; };
 
 constexpr int kTileH = 13;      // 8 rows of cells + 2 above + 3 below
 constexpr int kTileW = 40;      // 32 columns + 4 left + 4 right
-// Row stride of the tiles in shared memory (floats). 40 = dense. The experiment build of advect.cu
-// (-DKB_TILE_STRIDE=64, KAMINO_TILE_STRIDE=64 at run time) pads rows to 64: the bank of a cell is then
-// its column mod 32 whatever its row, so the lanes of a warp (distinct columns, one or two rows)
-// stop colliding (r01j ncu at C3: 27 % of the advection's shared-memory wavefronts are bank-conflict
-// replays with the dense layout, where rows are 8 banks apart).
-#ifndef KB_TILE_STRIDE
-#define KB_TILE_STRIDE 40
-#endif
-constexpr int kTileStride = KB_TILE_STRIDE;
+// Row stride of the tiles in shared memory (floats): dense. Measured and rejected (r02a A/B): rows padded
+// to 64 floats, which removes the bank conflicts between the rows of a warp's samples (27 % of the
+// shared-memory wavefronts in the r01j ncu capture) -- 33.9 instead of 33.5 us at 512 x 1024, 199.0 instead
+// of 197.7 us at 2048 x 4096: the kernel is bound by instruction issue, not by the shared-memory pipe.
+constexpr int kTileStride = kTileW;
 constexpr int kTileBytes = kTileH * kTileStride * 4;
 
 // The four corners of a cell from a shared-memory tile addressed by its 32-bit shared-window

@@ -151,7 +151,6 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
-    pdlTriggerTail(g);
     const int N = g.nPhi, half = N >> 1, log2T = g.log2NPhi - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
     const int pairs = (g.rowBegin + g.rowCount) >> 1;             // one past the last pair of the band
@@ -238,7 +237,6 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
-    pdlTriggerTail(g);
     const int N = g.nPhi, half = N >> 1, nT = g.nTheta, log2T = g.log2NPhi - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
     const int rowEnd = g.rowBegin + g.rowCount;
@@ -343,12 +341,6 @@ FftLaunch fftLaunch(const GridParams& g)
     return l;
 }
 
-int fftMinBlocks()
-{
-    static const int v = [] { const char* e = getenv("KAMINO_FFT_MINBLOCKS"); return e ? atoi(e) : 1; }();
-    return v;
-}
-
 template <int BLOCK, bool STAGE, int MINB>
 cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
                         const float* velPhiIn, const float* velThetaIn, float2* spectrum,
@@ -379,10 +371,9 @@ cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, c
     switch (l.block) {
     case 64: if (l.stage) KB_FFT(64, true); else KB_FFT(64, false);
     case 128: KB_FFT(128, true);
-    case 256:
-        // experiment switch: KAMINO_FFT_MINBLOCKS=3 caps the registers at 80 (three 256-thread blocks per SM)
-        if (fftMinBlocks() == 3) return fftDispatch<256, true, 3>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream);
-        KB_FFT(256, true);
+    // (r02a A/B: capping the 256-thread kernels at 80 registers for three blocks per SM is a loss at
+    // 2048 x 4096: forward 54.9 vs 47.5 us, inverse 64.3 vs 59.1 us)
+    case 256: KB_FFT(256, true);
     case 512: KB_FFT(512, false);
     case 1024: KB_FFT(1024, false);
     default: return cudaErrorInvalidValue;

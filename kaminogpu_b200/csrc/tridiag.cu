@@ -31,8 +31,6 @@
 // Layout: the half spectrum is solved in place in its [theta][slot] layout (no transposes).
 // A block owns W consecutive wavenumber slots and P * W threads (thread = chunk p, system w).
 // Tables are [slot group][row][w] so that every access of a warp is a run of W floats.
-#include <cstdlib>
-
 #include "kamino_kernels.cuh"
 
 namespace kb {
@@ -48,23 +46,15 @@ TriLaunch triLaunch(const GridParams& g, int batch)
     const int nT = g.nTheta, half = g.nPhi / 2;
     TriLaunch l;
     l.L = nT <= 64 ? 4 : nT <= 256 ? 8 : nT <= 1024 ? 16 : nT <= 4096 ? 32 : 64;
-    // experiment switch: KAMINO_TRI_L = chunk length (512 rows: 8 | 16 | 32; 2048 rows: 16 | 32 | 64)
-    if (const char* e = getenv("KAMINO_TRI_L")) {
-        const int want = atoi(e);
-        if ((nT == 512 && (want == 8 || want == 16 || want == 32)) || (nT == 2048 && (want == 16 || want == 32 || want == 64)))
-            l.L = want;
-    }
+    // (r02a A/B of the chunk length: 512 rows 10.4 / 10.0 / 13.4 us for L = 8 / 16 / 32; 2048 rows 63.3 / 51.0 /
+    // 75.4 us for L = 16 / 32 / 64)
     l.P = nT / l.L;
     // W: as wide as possible (64-byte runs) while the grid still has about one block per SM and
-    // the right-hand sides (nTheta * W float2) fit in shared memory (r01o A/B: W = 4 at 512 x 1024,
-    // W = 8 at 2048 x 4096)
+    // the right-hand sides (nTheta * W float2) fit in shared memory (r01o, r02a A/B: W = 4 at 512 x 1024
+    // (W = 2: 11.4 vs 10.0 us), W = 8 at 2048 x 4096 (W = 4: 63.7 vs 51.0 us))
     l.W = 8;
     while (l.W > 2 && ((long)(half / l.W) * batch < 128 || (size_t)nT * l.W * sizeof(float2) > 160 * 1024)) l.W >>= 1;
     while (l.P * l.W > (l.L >= 64 ? 512 : 1024)) l.W >>= 1;
-    if (const char* e = getenv("KAMINO_TRI_W")) {
-        const int w = atoi(e);
-        if ((w == 2 || w == 4 || w == 8) && l.P * w <= (l.L >= 64 ? 512 : 1024) && half % w == 0) l.W = w;
-    }
     l.smem = ((size_t)l.P * (l.L * l.W + l.W) + 2 * (size_t)(l.P + 1) * l.W) * sizeof(float2)
            + 2 * (size_t)l.P * l.W * sizeof(float);
     return l;
@@ -171,7 +161,6 @@ __global__ void __launch_bounds__(P * W)
 tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int pitch, int groupOffset)
 {
     extern __shared__ __align__(16) float2 sm[];
-    pdlTriggerTail(g);
     constexpr int nT = P * L;
     constexpr int kChunkPitch = L * W + W;              // float2 elements per chunk in smem
     constexpr int kThreads = P * W;
@@ -342,8 +331,6 @@ cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* sp
     KB_TRI_W(8, 16); KB_TRI_W(8, 32);                         // 128, 256
     KB_TRI_W(16, 32); KB_TRI_W(16, 64);                       // 512, 1024
     KB_TRI_W(32, 64);                                         // 2048
-    KB_TRI_W(8, 64); KB_TRI_W(32, 16);                        // 512 with KAMINO_TRI_L = 8 | 32
-    KB_TRI_W(16, 128); KB_TRI_W(64, 32);                      // 2048 with KAMINO_TRI_L = 16 | 64
     KB_TRI(2, 32, 128); KB_TRI(4, 32, 128); KB_TRI(8, 32, 128);   // 4096
     KB_TRI(2, 64, 128); KB_TRI(4, 64, 128);                   // 8192
 #undef KB_TRI_W

@@ -59,20 +59,26 @@ bool writeBgeo(const std::string& path, const std::vector<float>& positions,
     out.put8(0x00);              // end of extra section
     out.put8(0xff);
 
+    // Partio::write(file, parts) as the reference calls it (kernel/KaminoSolver.cu:356,400; forceCompressed
+    // defaults to false): compressed only when the name ends in ".gz" (partio_headers/Partio.h:289-290)
+    const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
 #ifdef KAMINO_HAVE_ZLIB
-    gzFile f = gzopen(path.c_str(), "wb");
-    if (!f) return false;
-    size_t done = 0;
-    while (done < out.bytes.size()) {
-        const unsigned chunk = (unsigned)((out.bytes.size() - done) < (1u << 30) ? (out.bytes.size() - done) : (1u << 30));
-        if (gzwrite(f, out.bytes.data() + done, chunk) != (int)chunk) { gzclose(f); return false; }
-        done += chunk;
+    if (gz) {
+        gzFile f = gzopen(path.c_str(), "wb");
+        if (!f) return false;
+        size_t done = 0;
+        while (done < out.bytes.size()) {
+            const unsigned chunk = (unsigned)((out.bytes.size() - done) < (1u << 30) ? (out.bytes.size() - done) : (1u << 30));
+            if (gzwrite(f, out.bytes.data() + done, chunk) != (int)chunk) { gzclose(f); return false; }
+            done += chunk;
+        }
+        return gzclose(f) == Z_OK;
     }
-    return gzclose(f) == Z_OK;
 #else
+    if (gz) return false;        // built without zlib
+#endif
     std::FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) return false;
     const bool ok = std::fwrite(out.bytes.data(), 1, out.bytes.size(), f) == out.bytes.size();
     return (std::fclose(f) == 0) && ok;
-#endif
 }

@@ -1,8 +1,9 @@
 // Minimal writer for Houdini "classic" binary geometry (.bgeo, version 5) point clouds: the
 // file format Partio's BGEO back end emits for the reference's write_data_bgeo /
-// write_particles_bgeo (kernel/KaminoSolver.cu:284-401). Big-endian; gzip-compressed like
-// Partio::write's default when built with zlib (-DKAMINO_HAVE_ZLIB), plain otherwise --
-// Partio's reader sniffs the gzip magic and accepts both.
+// write_particles_bgeo (kernel/KaminoSolver.cu:284-401). Big-endian, uncompressed -- Partio::write
+// compresses only when the file name ends in ".gz" or forceCompressed is set
+// (partio_headers/Partio.h:289-290), and the reference writes "<prefix><frame>.bgeo" with the
+// default arguments. A ".gz" name is gzip-compressed here too (needs -DKAMINO_HAVE_ZLIB).
 #pragma once
 
 #include <string>

@@ -48,11 +48,14 @@ void Kamino::run()
 
     float T = (firstFrame - 1) * DT;
     for (int i = firstFrame; i <= frames; i++) {
+        // the reference's loop (kernel/KaminoCore.cu:888-894) decides how many steps the frame takes; they
+        // are queued together so that the device runs them from 10-step graphs
+        int nFull = 0;
         while (T < i * DT) {
-            solver.stepForward(dt);
+            ++nFull;
             T += dt;
         }
-        solver.stepForward(dt + i * DT - T);
+        solver.stepFrame(dt, nFull, dt + i * DT - T);
         T = i * DT;
 
         std::cout << "Frame " << i << " is ready" << std::endl;

@@ -124,6 +124,26 @@ void KaminoSolver::stepForward(fReal timeStep)
     this->timeElapsed += timeStep;
 }
 
+// The steps of one frame of Kamino::run (kernel/KaminoCore.cu:888-894: `nFull` calls stepForward(dt) and
+// one stepForward(lastStep)) queued as ONE kamino_step call, i.e. as few CUDA-graph launches as the
+// step count allows (10 steps per graph) instead of one launch per step. Same state and same
+// bookkeeping as calling stepForward nFull + 1 times.
+void KaminoSolver::stepFrame(fReal dt, int nFull, fReal lastStep)
+{
+    if (phaseTiming) {
+        for (int k = 0; k < nFull; ++k) stepForward(dt);
+        stepForward(lastStep);
+        return;
+    }
+    const int n = nFull + 1;
+    KAMINO_CHECK(ctx, kamino_step(ctx, n));
+    if (particles) particles->swapGPUBuffers();
+    stepsTaken += (size_t)n;
+    for (int k = 0; k < nFull; ++k) this->timeElapsed += dt;
+    this->timeStep = lastStep;
+    this->timeElapsed += lastStep;
+}
+
 void KaminoSolver::synchronize() { KAMINO_CHECK(ctx, kamino_sync(ctx)); }
 
 // Raw checkpoint (no reference counterpart). State = u_phi, u_theta, density, particle

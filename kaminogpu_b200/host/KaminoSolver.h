@@ -63,6 +63,8 @@ public:
        error convention) on an unreadable file or a shape / dt / radius / particle-count mismatch. */
     void write_checkpoint(const std::string& path, unsigned frame);
     unsigned read_checkpoint(const std::string& path);
+    /* the steps of one output frame in one call (fewest graph launches): nFull steps of dt, then one of lastStep */
+    void stepFrame(fReal dt, int nFull, fReal lastStep);
     void setPhaseTiming(bool on) { phaseTiming = on; }   // default: env KAMINO_PHASE_TIMERS=1
     void synchronize();
     kamino_ctx* context() { return ctx; }

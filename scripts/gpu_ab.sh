@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of environment switches (VAR=a, or VAR1=a,VAR2=b for combinations) on the C2 / C3 bench lines.  gpurun -- 'bash scripts/gpu_ab.sh tag "VAR=a VAR=b ..." [workloads]'
-TAG=${1:-ab}; VARIANTS=${2:-"KAMINO_FORK=0 KAMINO_FORK=1"}; WL=${3:-"c2 c3"}
+TAG=${1:-ab}; VARIANTS=${2:-"KAMINO_NONE=0"}; WL=${3:-"c2 c3"}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 for v in $VARIANTS; do

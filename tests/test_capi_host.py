@@ -62,6 +62,21 @@ def test_particle_seeding_matches_reference_dump(lib, case, density):
     assert np.array_equal(pc, g["init.particles"])
 
 
+def test_particle_seeding_leaves_the_process_rand_state_alone(lib):
+    """The library restates glibc's rand() locally (csrc/host_init.cpp, GlibcRand): same sequence as libc's
+    never-seeded generator (checked against the oracle, which calls srand(1) / rand()), and no side effect
+    on the host program's generator."""
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(12345)
+    first = [libc.rand() for _ in range(3)]
+    libc.srand(12345)
+    n = lib.kamino_particle_count(16, ctypes.c_float(4.0))
+    mine = np.zeros(2 * n, np.float32)
+    assert lib.kamino_seed_particles_host(16, ctypes.c_float(4.0), oa.fptr(mine)) == 0
+    assert [libc.rand() for _ in range(3)] == first
+    assert np.array_equal(mine, oa.seed_particles(16, 4.0).ravel())
+
+
 def test_particle_counts_of_the_baseline_configs(lib):
     # SURVEY.md 8d: C1 particleDensity 200 -> 6,552,200 ; C2 particleDensity 2 -> 1,048,352
     assert lib.kamino_particle_count(128, ctypes.c_float(200.0)) == 6552200

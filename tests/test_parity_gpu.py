@@ -507,7 +507,7 @@ def test_live_reference_build_at_c2_size(K, tmp_path):
 
 def test_cli_runs_config_file(K, tmp_path):
     """The compiled drop-in: `kamino configKamino.txt` with the reference's grammar, output on,
-    produces gzip'd .bgeo frames and the reference's progress lines."""
+    produces plain (uncompressed, as Partio::write does for a .bgeo name) classic-bgeo frames and the reference's progress lines."""
     import gzip
     import os
     import struct
@@ -521,7 +521,7 @@ def test_cli_runs_config_file(K, tmp_path):
     assert "Frame 2 is ready" in out.stdout and "frames per second" in out.stdout
     for stem, npts in (("f", 32 * 64), ("p", 8192)):
         for frame in (0, 1, 2):
-            raw = gzip.open(str(tmp_path / "out" / ("%s%d.bgeo" % (stem, frame)))).read()
+            raw = open(str(tmp_path / "out" / ("%s%d.bgeo" % (stem, frame))), "rb").read()
             assert raw[:5] == b"BgeoV"
             version, points = struct.unpack(">ii", raw[5:13])
             assert version == 5 and points == npts
@@ -548,8 +548,8 @@ def test_cli_image_driven_initialisation(K, tmp_path):
     def read_bgeo(path):
         """-> {attribute name: (points x count) float32}, points (positions are implicit, 4 floats)."""
         import struct
-        raw = gzip.open(path).read()
-        assert raw[:5] == b"BgeoV"
+        raw = open(path, "rb").read()
+        assert raw[:5] == b"BgeoV"          # plain bytes: Partio compresses only *.gz names
         version, points, _, _, _, nattr, _, _, _ = struct.unpack(">9i", raw[5:41])
         pos, attrs = 41, []
         for _ in range(nattr):
@@ -572,7 +572,6 @@ def test_cli_image_driven_initialisation(K, tmp_path):
     assert parts["color"].shape == (2048, 3) and parts["color"].max() > 0.0      # particles are not black
 
 
-@pytest.mark.xfail(reason="written after this round's GPU budget was spent: not yet run on hardware", strict=False)
 @pytest.mark.timeout(600)
 def test_cli_restart_from_checkpoint_continues_bit_for_bit(K, tmp_path):
     """KAMINO_CHECKPOINT / KAMINO_RESTART (raw state checkpoint): frames 1-2 with a
@@ -602,40 +601,10 @@ def test_cli_restart_from_checkpoint_continues_bit_for_bit(K, tmp_path):
     assert "Resuming after frame 2" in stdout
     for stem in ("f", "p"):
         for frame in (1, 2):
-            assert gzip.open(str(first / ("%s%d.bgeo" % (stem, frame)))).read() == gzip.open(str(whole / ("%s%d.bgeo" % (stem, frame)))).read()
+            assert open(str(first / ("%s%d.bgeo" % (stem, frame))), "rb").read() == open(str(whole / ("%s%d.bgeo" % (stem, frame))), "rb").read()
         for frame in (3, 4):
-            assert gzip.open(str(second / ("%s%d.bgeo" % (stem, frame)))).read() == gzip.open(str(whole / ("%s%d.bgeo" % (stem, frame)))).read()
+            assert open(str(second / ("%s%d.bgeo" % (stem, frame))), "rb").read() == open(str(whole / ("%s%d.bgeo" % (stem, frame))), "rb").read()
         assert not os.path.exists(str(second / ("%s0.bgeo" % stem)))
-
-
-def test_forked_particles_mode_is_bit_identical(K, tmp_path):
-    """KAMINO_FORK_PARTICLES=1 (particles as their own kernel on a parallel graph branch, three
-    rotating velocity buffers) must produce the bits of the default fused launch."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = (
-        "import sys, numpy as np\n"
-        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "import oracle_api as oa\n"
-        "from kaminogpu_b200.solver import KaminoSolver\n"
-        "g = oa.golden('t32'); nT = 32\n"
-        "s = KaminoSolver(64, nT, float(g['meta.radius']), float(g['meta.dt']))\n"
-        "s.density.cpuBuffer[:] = g['init.density'].reshape(nT, 64); s.density.copyToGPU()\n"
-        "s.initParticlesfromPic('', 0, coords=g['init.particles'])\n"
-        "s.stepForward(nSteps=13); s.advection(); s.geometric(); s.projection(); s.stepForward(nSteps=2); s.sync()\n"
-        "np.savez(sys.argv[1], u=s.velPhi.copyBackToCPU(), v=s.velTheta.copyBackToCPU(), r=s.density.copyBackToCPU(), p=s.particles.copyBack2CPU())\n"
-    ) % (root, os.path.join(root, "tests"))
-    outs = []
-    for fork in ("0", "1"):
-        path = str(tmp_path / ("state%s.npz" % fork))
-        env = dict(os.environ, KAMINO_FORK_PARTICLES=fork)
-        run = subprocess.run([sys.executable, "-c", script, path], env=env, capture_output=True, text=True, timeout=600)
-        assert run.returncode == 0, run.stderr[-2000:]
-        outs.append(np.load(path))
-    for name in ("u", "v", "r", "p"):
-        assert np.array_equal(outs[0][name].view(np.uint32), outs[1][name].view(np.uint32)), name
 
 
 # ---- theta-band decomposition (SURVEY.md 8e): virtual ranks on one GPU ----------------------------
@@ -668,8 +637,6 @@ def test_banded_step_is_bit_identical_to_single_gpu(K, nT, world):
     assert np.array_equal(rho.ravel(), ref["density"])
 
 
-@pytest.mark.xfail(reason="written after this round's GPU budget was spent: the band-local solve has not run on hardware yet",
-                   strict=False)
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
 def test_banded_spike_mode_tracks_single_gpu(K, nT, world):
