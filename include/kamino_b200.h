@@ -213,6 +213,12 @@ int kamino_debug_locate(kamino_ctx* ctx, int kind, long n, const float* phiRaw, 
                         int32_t* phiIndex, int32_t* thetaIndex, float* alphaPhi, float* alphaTheta,
                         float* phiValidated, float* thetaValidated, int32_t* flags);
 
+/* kamino_project with the theta solve performed in the reference's own operation order (cyclic reduction in
+ * fp32, kernel/tdm.cu:3-96) instead of the product's LU recurrences: lets a test show that the distance
+ * between the two builds' pressure is the reference's CR rounding. nTheta <= 2048 (the reference's launch
+ * limit, kernel/KaminoCore.cu:779-784). Test use only; never part of kamino_step. */
+int kamino_debug_project_cr(kamino_ctx* ctx);
+
 /* Library build information: "kamino_b200 <version> sm_100a". */
 const char* kamino_version(void);
 

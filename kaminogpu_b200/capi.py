@@ -65,6 +65,7 @@ SIGNATURES = {
     "kamino_debug_locate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "kamino_debug_project_cr": (ctypes.c_int, [ctypes.c_void_p]),
     "kamino_version": (ctypes.c_char_p, []),
     "kamino_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
     "kamino_host_free": (ctypes.c_int, [ctypes.c_void_p]),

@@ -556,6 +556,20 @@ int kamino_project(kamino_ctx* ctx)
     return timedPhase(ctx, ctx->projectionTime, [&](IndexState& st) { return enqueueProject(ctx, st, ctx->stream); });
 }
 
+// Parity instrumentation: kamino_project with the theta solve done in the reference's cyclic-reduction order
+// (debug_cr.cu). Never part of a step graph.
+int kamino_debug_project_cr(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (ctx->g.nTheta > 2048) return fail(ctx, KAMINO_ERR_INVALID, "the reference's cyclic reduction cannot launch above nTheta = 2048");
+    return timedPhase(ctx, ctx->projectionTime, [&](IndexState& st) {
+        cudaError_t e = enqueueProjectPart(ctx, st, 0, ctx->stream);
+        if (e == cudaSuccess) e = launchCyclicReductionDebug(ctx->g, ctx->tables, ctx->spectrum, ctx->batch, ctx->stream);
+        if (e == cudaSuccess) e = enqueueProjectPart(ctx, st, 2, ctx->stream);
+        return e;
+    });
+}
+
 // ---- theta-band entry points (band-decomposed multi-GPU runs, kaminogpu_b200/banded.py) ----------
 
 static int bandRange(kamino_ctx* ctx, int rowBegin, int rowCount, int multiple, GridParams* out)

@@ -101,6 +101,9 @@ cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& 
                                      float* velPhi, float* velTheta, float* pressure, int batch,
                                      cudaStream_t stream);
 
+// parity instrumentation (debug_cr.cu): the theta solve in the reference's cyclic-reduction order, in place
+cudaError_t launchCyclicReductionDebug(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, cudaStream_t stream);
+
 // host: the constants block of the samplers for this grid
 void fillSamplerConsts(const GridParams& g, void* hostBlock64);
 

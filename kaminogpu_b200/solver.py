@@ -199,6 +199,10 @@ class KaminoSolver:
     def projection(self):
         capi.check(self._lib.kamino_project(self._ctx), self._ctx)
 
+    def projection_cr_order(self):
+        """Parity instrumentation: the projection with the reference's cyclic-reduction theta solve."""
+        capi.check(self._lib.kamino_debug_project_cr(self._ctx), self._ctx)
+
     def stepForward(self, timeStep=None, nSteps=1):
         """kernel/KaminoSolver.cu:197-221. The argument is recorded and otherwise ignored,
         exactly as the reference's kernels ignore it."""
