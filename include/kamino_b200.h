@@ -192,11 +192,53 @@ int kamino_launches_per_step(const kamino_ctx* ctx);
  * brackets (kernel/KaminoSolver.cu:201-218). Synchronous. */
 int kamino_profile_steps(kamino_ctx* ctx, int nSteps, float* kernelSeconds);
 
+/* ---- theta-band decomposition of one simulation over P GPUs (BASELINE config 5) -------------------------
+ * No reference counterpart: the reference is single-GPU (kernel/KaminoSolver.cu:20) and cannot launch its
+ * theta solve above nTheta = 2048 (kernel/KaminoCore.cu:779-784). One kamino_dist per GPU (one process per
+ * GPU, or one thread per GPU): rank r owns theta rows [r nTheta/P, (r+1) nTheta/P) and the same range of
+ * wavenumber slots, holds band-sized buffers only, and kamino_dist_step runs the whole step loop in C++:
+ * NCCL halo exchange (24 rows of u_phi, u_theta, density per neighbour), advection / geometric /
+ * divergence + FFT on the band, NCCL transpose, theta solve of the rank's wavenumbers, transpose back,
+ * inverse FFT + gradient (csrc/dist.cu). Same kernels and arithmetic as kamino_step: bit-identical to the
+ * single-GPU run. No tracer particles (they would migrate between ranks).
+ *
+ * Bootstrap: rank 0 calls kamino_dist_unique_id and hands the 128 bytes to the other ranks by any means
+ * (torch.distributed broadcast in bench.py, MPI_Bcast, a file); every rank then calls kamino_dist_create
+ * with it (collective: ncclCommInitRank). id128 = NULL creates a rank without a communicator: P such ranks
+ * on one device are stepped by kamino_dist_group_step (device copies instead of NCCL; tests).
+ * world: power of two, >= 32 rows and a multiple of 8 wavenumbers per rank. */
+typedef struct kamino_dist kamino_dist;
+int kamino_dist_unique_id(void* id128);
+int kamino_dist_create(kamino_dist** out, int device, int nTheta, float radius, float dt, int rank, int world,
+                       const void* id128);
+int kamino_dist_destroy(kamino_dist* d);
+const char* kamino_dist_last_error(const kamino_dist* d);
+/* rows [rowBegin, rowEnd) and wavenumber slots [slotBegin, slotEnd) of this rank; bytes of device memory held */
+int kamino_dist_shape(const kamino_dist* d, int* rowBegin, int* rowEnd, int* slotBegin, int* slotEnd, size_t* deviceBytes);
+/* the rank's OWN rows of a field (dense, rows x nPhi; u_theta: the rows below nTheta - 1) <-> host; synchronous */
+int kamino_dist_upload(kamino_dist* d, int field, const float* hostRows);
+int kamino_dist_download(kamino_dist* d, int field, float* hostRows);
+/* nSteps steps of the band-decomposed simulation; collective over the communicator, asynchronous */
+int kamino_dist_step(kamino_dist* d, int nSteps);
+int kamino_dist_group_step(kamino_dist* const* ranks, int world, int nSteps);
+/* Blocks until the rank's work is complete. Returns KAMINO_ERR_STATE if a backtrace left the 24-row halo
+ * since the last call (theta-CFL too large for the decomposition: the run no longer equals the single-GPU one). */
+int kamino_dist_sync(kamino_dist* d);
+int kamino_dist_stream(kamino_dist* d, void** cudaStream);
+/* Communication accounting. enable = 1 / 0 switches per-step CUDA-event brackets around the NCCL calls on / off
+ * (it adds one host synchronisation per step; -1 leaves the setting); the accumulated seconds and bytes SENT per
+ * step by this rank are returned. */
+int kamino_dist_comm_stats(kamino_dist* d, int enable, double* haloSeconds, double* transposeSeconds, long* steps,
+                           size_t* haloBytesPerStep, size_t* transposeBytesPerStep);
+
 /* ---- host-side initialisers (pure CPU; reproduce the reference's initial state) ------ */
 
 /* KaminoSolver::initialize_velocity (kernel/KaminoInitializer.cu:3-134): FBM curl-noise
  * initial u_phi (nTheta x nPhi) and u_theta ((nTheta-1) x nPhi). */
 int kamino_init_velocity_host(int nTheta, float radius, float* velPhi, float* velTheta);
+/* The same field for rows [rowBegin, rowBegin + rowCount) only (a band of a decomposed run): velPhi receives
+ * rowCount rows, velTheta the rows of the range below nTheta - 1. Every cell is a pure function of its position. */
+int kamino_init_velocity_host_rows(int nTheta, float radius, int rowBegin, int rowCount, float* velPhi, float* velTheta);
 /* KaminoParticles constructor (kernel/KaminoParticles.cu:20-62): particle count for a
  * density, and the jittered lattice driven by libc rand() in the reference's call order
  * (the generator is put into its never-seeded state first). */

@@ -60,6 +60,25 @@ SIGNATURES = {
     "kamino_launches_per_step": (ctypes.c_int, [ctypes.c_void_p]),
     "kamino_profile_steps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p]),
     "kamino_init_velocity_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "kamino_init_velocity_host_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "kamino_dist_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_dist_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "kamino_dist_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_dist_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "kamino_dist_shape": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                         ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                         ctypes.POINTER(ctypes.c_size_t)]),
+    "kamino_dist_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "kamino_dist_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "kamino_dist_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "kamino_dist_group_step": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]),
+    "kamino_dist_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_dist_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "kamino_dist_comm_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
+                                              ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "kamino_particle_count": (ctypes.c_long, [ctypes.c_int, ctypes.c_float]),
     "kamino_seed_particles_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_void_p]),
     "kamino_debug_locate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,

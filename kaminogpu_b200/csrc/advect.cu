@@ -257,9 +257,10 @@ __global__ void locateKernel(const SamplerConsts* __restrict__ consts, long n, c
 
 } // namespace
 
-void fillSamplerConsts(const GridParams& g, void* hostBlock64)
+void fillSamplerConsts(const GridParams& g, void* hostBlock64, int validLo, int validHi, int* haloViolation)
 {
     SamplerConsts c{};
+    c.validLo = validLo; c.validHi = validHi < 0 ? g.nTheta : validHi; c.haloViolation = haloViolation;
     c.h = g.h; c.halfH = g.halfH; c.invH = g.invH;
     c.N = g.nPhi; c.mask = g.nPhi - 1; c.halfN = g.nPhi >> 1; c.nTheta = g.nTheta;
     auto bits = [](float x) { unsigned u; memcpy(&u, &x, 4); return u; };

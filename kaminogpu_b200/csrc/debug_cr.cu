@@ -6,7 +6,7 @@
 // an fp64 solve than the reference's own CR. The distance between the two builds' pressure is therefore
 // the reference's CR rounding error; this kernel exists so that a TEST can show that: with the solve done
 // in CR order (same elimination order, same fused multiply-adds as the reference's SASS: b - c*t1 - a*t2
-// contracts to two FFMAs, see oracle/kamino_oracle.c ko_cyclic_reduction), u_theta and the pressure fall
+// contracts to two FFMAs), the pressure falls
 // within the north-star 1e-5 of the reference's dump. kamino_debug_project_cr (kamino_ctx.cu) runs
 // divergence+FFT -> this kernel -> inverse FFT+gradient; it is never captured into a step graph.
 #include "kamino_kernels.cuh"

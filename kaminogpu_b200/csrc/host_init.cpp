@@ -62,7 +62,15 @@ float fbm(float x, float y)
 
 extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi, float* velTheta)
 {
-    if (nTheta < 2 || !velPhi || !velTheta) return KAMINO_ERR_INVALID;
+    return kamino_init_velocity_host_rows(nTheta, radius, 0, nTheta, velPhi, velTheta);
+}
+
+extern "C" int kamino_init_velocity_host_rows(int nTheta, float radius, int rowBegin, int rowCount, float* velPhi, float* velTheta)
+{
+    if (nTheta < 2 || !velPhi || !velTheta || rowBegin < 0 || rowCount < 1 || rowBegin + rowCount > nTheta) return KAMINO_ERR_INVALID;
+    const int rowEnd = rowBegin + rowCount;
+    velPhi -= (size_t)rowBegin * (2 * (size_t)nTheta);          // global row indexing below
+    velTheta -= (size_t)rowBegin * (2 * (size_t)nTheta);
     const int nPhi = 2 * nTheta;
     const float h = (float)(kTwoPi / (double)nPhi);           // the solver's gridLen, KaminoSolver.cu:14
     const float gain = (float)(4096.0 / (double)nPhi);        // KaminoInitializer.cu:9
@@ -73,7 +81,7 @@ extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi
     // function of its position, so the rows are spread over the host cores (the reference's serial
     // double loop takes minutes at 8192 x 16384; the values do not depend on the schedule).
 #pragma omp parallel for schedule(dynamic, 8)
-    for (int j = 0; j < nTheta; ++j) {
+    for (int j = rowBegin; j < rowEnd; ++j) {
         const float yUp = (float)(j + 1) * h, yLo = (float)j * h;
         for (int i = 0; i < nPhi; ++i) {
             const float xR = (i == 0) ? h / 2 : (float)i * h + h / 2;
@@ -86,7 +94,7 @@ extern "C" int kamino_init_velocity_host(int nTheta, float radius, float* velPhi
     // u_theta: minus the phi-difference; the reference's lower-left sample reuses the upper
     // row (KaminoInitializer.cu:69), which is kept
 #pragma omp parallel for schedule(dynamic, 8)
-    for (int j = 1; j < nTheta; ++j) {
+    for (int j = rowBegin + 1; j < (rowEnd + 1 < nTheta ? rowEnd + 1 : nTheta); ++j) {   // u_theta row j - 1
         const float yUp = (float)j * h + h / 2, yLo = (float)j * h - h / 2;
         for (int i = 0; i < nPhi; ++i) {
             const float xR = (float)(i + 1) * h, xL = (float)i * h;

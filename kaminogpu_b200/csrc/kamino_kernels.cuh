@@ -75,14 +75,23 @@ size_t spectralTableBytes(const GridParams& g);
 size_t solveTableFloats(const GridParams& g);
 cudaError_t configureTridiagonal(const GridParams& g, int batch);
 // runs after launchBuildTables (same stream): LU factorisation of every wavenumber's system, once
-cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream);
+// (slotBegin, slotCount: build the tables of a wavenumber band only, indexed from 0; default: every slot)
+cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream,
+                                   int slotBegin = 0, int slotCount = -1);
 cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_t stream);
 
 // spectrum layout: S[sim][j][k], k = 0 .. nPhi/2-1, float2; slot k holds wavenumber
 // n = k for k >= 1 and the Nyquist mode n = nPhi/2 in slot 0 (the n = 0 mode is never
 // projected by the reference, kernel/KaminoSolver.cu:154-159 + KaminoCore.cu:692-700).
+// Theta-band runs (dist.cu) keep the half spectrum in the layouts of the transposes around the theta solve
+// instead of dense [row][slot]: slots are grouped into blocks of 2^log2Block (one block per destination /
+// source rank), element (row, k) sits at (k >> log2Block) * blockPitch + (row - rowBase) * rowPitch +
+// (k & (2^log2Block - 1)). The forward FFT stores straight into the send buffer of the all-to-all and the
+// inverse FFT reads straight from its receive buffer: no pack / unpack passes.
+struct SpectrumLayout { int rowBase, rowPitch, log2Block; size_t blockPitch; };
 cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, const float* velPhi,
-                                const float* velTheta, float2* spectrum, int batch, cudaStream_t stream);
+                                const float* velTheta, float2* spectrum, int batch, cudaStream_t stream,
+                                const SpectrumLayout* packed = nullptr);
 cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
                               cudaStream_t stream);
 // band-decomposed runs: solve slots [slotBegin, slotBegin + slotCount) whose right-hand sides sit in
@@ -99,13 +108,14 @@ cudaError_t launchBandLocalSolve(const GridParams& g, const SpectralTables& band
 // velPhi / velTheta updated in place; pressure (may be NULL) receives p.
 cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
                                      float* velPhi, float* velTheta, float* pressure, int batch,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, const SpectrumLayout* packed = nullptr);
 
 // parity instrumentation (debug_cr.cu): the theta solve in the reference's cyclic-reduction order, in place
 cudaError_t launchCyclicReductionDebug(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, cudaStream_t stream);
 
 // host: the constants block of the samplers for this grid
-void fillSamplerConsts(const GridParams& g, void* hostBlock64);
+// (validLo, validHi, haloViolation: the resident row range and the device flag of a theta-band context, dist.cu)
+void fillSamplerConsts(const GridParams& g, void* hostBlock64, int validLo = 0, int validHi = -1, int* haloViolation = nullptr);
 
 // One-time setup of kernel attributes (opt-in shared memory); called at context creation.
 cudaError_t configureKernels(const GridParams& g, int batch);

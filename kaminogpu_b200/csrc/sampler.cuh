@@ -88,12 +88,18 @@ __device__ __forceinline__ float lerpFast(float from, float to, float alpha, flo
 // LDC/LDCU per sample in the r01e profile of this issue-bound kernel), but it never re-issues a
 // global load.
 struct SamplerConsts {               // 16 words, 16-byte aligned
-    float h, halfH, invH, pad0;
+    float h, halfH, invH;
+    int validLo;                     // first field row held in memory (0 unless the context is a theta band)
     int N, mask, halfN, nTheta;
     // interior fast path: shifted theta in [thetaLo, thetaHi[kind]) and shifted phi in [phiLo, 2 pi)
     // as unsigned ranges on the bit patterns: (bits - lo) < span
-    unsigned thetaLoBits, thetaSpanCentred, thetaSpanVTheta, pad1;
-    unsigned phiLoBits, phiSpan, pad2, pad3;
+    unsigned thetaLoBits, thetaSpanCentred, thetaSpanVTheta;
+    int validHi;                     // one past the last row held in memory (nTheta unless a theta band)
+    unsigned phiLoBits, phiSpan;
+    // Band-decomposed runs (dist.cu) hold rows [validLo, validHi) only. A gather of the general path that
+    // would leave them (a backtrace longer than the halo: theta-CFL too large for the halo width) is
+    // clamped into memory and recorded here; the host checks the flag at the next synchronisation.
+    int* haloViolation;              // NULL when the whole grid is resident
 };
 
 struct SamplerRegs {
@@ -106,7 +112,7 @@ struct SamplerRegs {
         const float4 a = __ldg(reinterpret_cast<const float4*>(c));
         const int4 b = __ldg(reinterpret_cast<const int4*>(c) + 1);
         const uint4 d = __ldg(reinterpret_cast<const uint4*>(c) + 2);
-        const uint4 e = __ldg(reinterpret_cast<const uint4*>(c) + 3);
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(c) + 6);
         h = a.x; halfH = a.y; invH = a.z;
         N = b.x; mask = b.y; halfN = b.z; nTheta = b.w;
         thetaLoBits = d.x; thetaSpanCentred = d.y; thetaSpanVTheta = d.z;
@@ -161,8 +167,8 @@ __device__ __forceinline__ bool poleBranch(const SamplerRegs& g, const Location&
 // bit patterns (-0.0f and NaN fall through to validateCoord, which treats them as the
 // reference does).
 template <int KIND>
-__device__ __forceinline__ float sampleGeneralInline(const SamplerRegs& g, const float* __restrict__ field,
-                                                     float phiRaw, float thetaRaw)
+__device__ __forceinline__ float sampleGeneralInline(const SamplerRegs& g, const SamplerConsts* __restrict__ consts,
+                                                     const float* __restrict__ field, float phiRaw, float thetaRaw)
 {
     const Location loc = locate<KIND>(g, phiRaw, thetaRaw);
     const int phiIndex = loc.phiIndex, thetaIndex = loc.thetaIndex;
@@ -174,7 +180,15 @@ __device__ __forceinline__ float sampleGeneralInline(const SamplerRegs& g, const
     // rows past the array are clamped to the last one: the reference reads out of bounds
     // there (undefined; only reachable when the theta-CFL exceeds 1 at the south pole)
     const bool oneRow = pole || thetaIndex > lastRow;
-    const int rowLo = min(thetaIndex, lastRow);
+    int rowLo = min(thetaIndex, lastRow);
+    if (consts->haloViolation) {
+        // theta band: rows [validLo, validHi) are resident (cold path: one extra load of the constants block)
+        const int lo = consts->validLo, hi = consts->validHi - (oneRow ? 1 : 2);
+        if (rowLo < lo || rowLo > hi) {
+            atomicOr(consts->haloViolation, 1);
+            rowLo = max(lo, min(rowLo, hi));
+        }
+    }
     const int colShift = pole ? g.halfN : 0;             // second belt = same row at phi + pi
     const int rowStep = oneRow ? 0 : N;
     const int c0 = phiIndex & mask;                         // size_t % nPhi, nPhi = 2^k
@@ -211,7 +225,7 @@ __device__ __noinline__ float sampleGeneral(const SamplerConsts* __restrict__ co
                                             float phiRaw, float thetaRaw)
 {
     const SamplerRegs g(consts);
-    return sampleGeneralInline<KIND>(g, field, phiRaw, thetaRaw);
+    return sampleGeneralInline<KIND>(g, consts, field, phiRaw, thetaRaw);
 }
 
 // The sample as the kernels call it, split in two so that the gathers of several independent

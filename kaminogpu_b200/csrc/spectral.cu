@@ -144,10 +144,10 @@ __device__ __forceinline__ uint64_t* stageTwiddles(const float2* __restrict__ tw
 // Each transform handles a pair of theta rows (z = div_j + i div_{j+1}) with T = N/16 threads;
 // a block of BLOCK threads holds BLOCK/T transforms. grid (ceil(nTheta/2 / (BLOCK/T)), batch),
 // dynamic smem: [twiddles N float2 if STAGE] + (BLOCK/T) * paddedSize(N) float2.
-template <int BLOCK, bool STAGE, int MINB>
+template <int BLOCK, bool STAGE, int MINB, bool PACKED>
 __global__ void __launch_bounds__(BLOCK, MINB)
 divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ velPhiAll,
-                    const float* __restrict__ velThetaAll, float2* __restrict__ spectrumAll)
+                    const float* __restrict__ velThetaAll, float2* __restrict__ spectrumAll, SpectrumLayout lay)
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
@@ -207,11 +207,13 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
     // kernel/KaminoCore.cu:652-653); only k = 1 .. N/2 is kept, the Nyquist mode in slot 0.
     if (!valid) return;
     const float scale = 0.5f / (float)N;
-    float2* rowA = spectrum + (size_t)j * half;
-    float2* rowB = spectrum + (size_t)(j + 1) * half;
+    // dense: [row][slot]; PACKED (theta bands, dist.cu): the send layout of the transpose, see SpectrumLayout
+    float2* rowA = PACKED ? spectrum + (size_t)(j - lay.rowBase) * lay.rowPitch : spectrum + (size_t)j * half;
+    float2* rowB = rowA + (PACKED ? lay.rowPitch : half);
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         const int k = tt + (m << log2T);          // 0 .. N/2-1
+        const size_t at = PACKED ? (size_t)(k >> lay.log2Block) * lay.blockPitch + (k & ((1 << lay.log2Block) - 1)) : (size_t)k;
         if (k == 0) {
             const float2 zn = v[8];                // Z[N/2] (tt = 0): both rows real
             rowA[0] = make_float2(2.0f * scale * zn.x, 0.0f);
@@ -219,8 +221,8 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
         } else {
             const float2 zk = v[m], zc = buf[fft::pad(N - k)];
             // A_k = (Z_k + conj Z_{N-k}) / 2,  B_k = (Z_k - conj Z_{N-k}) / (2i)
-            rowA[k] = make_float2(scale * (zk.x + zc.x), scale * (zk.y - zc.y));
-            rowB[k] = make_float2(scale * (zk.y + zc.y), scale * (zc.x - zk.x));
+            rowA[at] = make_float2(scale * (zk.x + zc.x), scale * (zk.y - zc.y));
+            rowB[at] = make_float2(scale * (zk.y + zc.y), scale * (zc.x - zk.x));
         }
     }
 }
@@ -229,11 +231,11 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
 
 // One transform per theta row with T = N/16 threads, BLOCK/T rows per block.
 // grid (ceil(nTheta / (BLOCK/T)), batch), dynamic smem as for the forward kernel.
-template <int BLOCK, bool STAGE, int MINB>
+template <int BLOCK, bool STAGE, int MINB, bool PACKED>
 __global__ void __launch_bounds__(BLOCK, MINB)
 inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restrict__ spectrumAll,
                          float* __restrict__ velPhiAll, float* __restrict__ velThetaAll,
-                         float* __restrict__ pressureAll)
+                         float* __restrict__ pressureAll, SpectrumLayout lay)
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
@@ -250,8 +252,8 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
     float* velPhi = velPhiAll + (size_t)sim * g.cells + (size_t)j * N;
     float* velTheta = velThetaAll + (size_t)sim * g.cells + (size_t)j * N;
     const bool hasSouth = (j < nT - 1);
-    const float2* rowU = spectrum + (size_t)j * half;
-    const float2* rowS = spectrum + (size_t)(hasSouth ? j + 1 : j) * half;     // !hasSouth: Y = 0
+    const float2* rowU = PACKED ? spectrum + (size_t)(j - lay.rowBase) * lay.rowPitch : spectrum + (size_t)j * half;
+    const float2* rowS = hasSouth ? rowU + (PACKED ? lay.rowPitch : half) : rowU;     // !hasSouth: Y = 0
 
     uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, g.log2NPhi));
     const float2* tw = STAGE ? twShared : t.twiddle;
@@ -268,8 +270,9 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
         for (int e = 0; e < 8; ++e) {
             const int idx = tt + ((h * 8 + e) << log2T);
             const int slot = (h == 0) ? idx : ((N - idx) & (half - 1));     // idx = N/2 -> 0
-            x[e] = __ldg(rowU + slot);
-            sth[e] = __ldg(rowS + slot);
+            const size_t at = PACKED ? (size_t)(slot >> lay.log2Block) * lay.blockPitch + (slot & ((1 << lay.log2Block) - 1)) : (size_t)slot;
+            x[e] = __ldg(rowU + at);
+            sth[e] = __ldg(rowS + at);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -341,33 +344,47 @@ FftLaunch fftLaunch(const GridParams& g)
     return l;
 }
 
-template <int BLOCK, bool STAGE, int MINB>
-cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
-                        const float* velPhiIn, const float* velThetaIn, float2* spectrum,
-                        float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream)
+template <int BLOCK, bool STAGE, int MINB, bool PACKED>
+cudaError_t fftDispatchLayout(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
+                              const float* velPhiIn, const float* velThetaIn, float2* spectrum,
+                              float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream, const SpectrumLayout& lay)
 {
     if (which == 0) {           // configure
-        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE, MINB, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE, MINB, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
     }
     if (which == 1) {
         const int pairs = g.rowCount / 2;
         dim3 grid((pairs + l.perBlock - 1) / l.perBlock, batch);
-        return launchChained(divergenceFFTKernel<BLOCK, STAGE, MINB>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum);
+        return launchChained(divergenceFFTKernel<BLOCK, STAGE, MINB, PACKED>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum, lay);
     } else {
         dim3 grid((g.rowCount + l.perBlock - 1) / l.perBlock, batch);
-        return launchChained(inverseFFTGradientKernel<BLOCK, STAGE, MINB>, grid, dim3(BLOCK), l.smem, stream, g, t,
-                             (const float2*)spectrum, velPhi, velTheta, pressure);
+        return launchChained(inverseFFTGradientKernel<BLOCK, STAGE, MINB, PACKED>, grid, dim3(BLOCK), l.smem, stream, g, t,
+                             (const float2*)spectrum, velPhi, velTheta, pressure, lay);
     }
+}
+
+template <int BLOCK, bool STAGE, int MINB>
+cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
+                        const float* velPhiIn, const float* velThetaIn, float2* spectrum,
+                        float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream, const SpectrumLayout* lay)
+{
+    if (which == 0) {           // configure both addressing variants
+        cudaError_t e = fftDispatchLayout<BLOCK, STAGE, MINB, false>(0, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
+        if (e != cudaSuccess) return e;
+        return fftDispatchLayout<BLOCK, STAGE, MINB, true>(0, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
+    }
+    if (lay) return fftDispatchLayout<BLOCK, STAGE, MINB, true>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, *lay);
+    return fftDispatchLayout<BLOCK, STAGE, MINB, false>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
 }
 
 cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, const float* velPhiIn,
                       const float* velThetaIn, float2* spectrum, float* velPhi, float* velTheta,
-                      float* pressure, int batch, cudaStream_t stream)
+                      float* pressure, int batch, cudaStream_t stream, const SpectrumLayout* lay = nullptr)
 {
     const FftLaunch l = fftLaunch(g);
-#define KB_FFT(B, S) return fftDispatch<B, S, 0>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream)
+#define KB_FFT(B, S) return fftDispatch<B, S, 0>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, lay)
     switch (l.block) {
     case 64: if (l.stage) KB_FFT(64, true); else KB_FFT(64, false);
     case 128: KB_FFT(128, true);
@@ -392,16 +409,17 @@ cudaError_t configureKernels(const GridParams& g, int batch)
 }
 
 cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, const float* velPhi,
-                                const float* velTheta, float2* spectrum, int batch, cudaStream_t stream)
+                                const float* velTheta, float2* spectrum, int batch, cudaStream_t stream,
+                                const SpectrumLayout* packed)
 {
-    return fftSelect(1, g, t, velPhi, velTheta, spectrum, nullptr, nullptr, nullptr, batch, stream);
+    return fftSelect(1, g, t, velPhi, velTheta, spectrum, nullptr, nullptr, nullptr, batch, stream, packed);
 }
 
 cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& t, const float2* spectrum,
                                      float* velPhi, float* velTheta, float* pressure, int batch,
-                                     cudaStream_t stream)
+                                     cudaStream_t stream, const SpectrumLayout* packed)
 {
-    return fftSelect(2, g, t, nullptr, nullptr, const_cast<float2*>(spectrum), velPhi, velTheta, pressure, batch, stream);
+    return fftSelect(2, g, t, nullptr, nullptr, const_cast<float2*>(spectrum), velPhi, velTheta, pressure, batch, stream, packed);
 }
 
 } // namespace kb

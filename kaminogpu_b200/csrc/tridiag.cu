@@ -62,12 +62,16 @@ TriLaunch triLaunch(const GridParams& g, int batch)
 
 // ---- setup: LU factors and chunk products, one thread per wavenumber slot, fp64 -------------------
 
-__global__ void buildSolveTablesKernel(GridParams g, SpectralTables t, int W, int L)
+// (slotBegin, slotCount): the slots this table set covers -- all of them, or the wavenumber band of one rank of
+// a theta-band run (dist.cu), whose tables are indexed by slot - slotBegin.
+__global__ void buildSolveTablesKernel(GridParams g, SpectralTables t, int W, int L, int slotBegin, int slotCount)
 {
     const int nT = g.nTheta, half = g.nPhi >> 1;
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= half) return;
-    const int n = (slot == 0) ? half : slot;        // wavenumber of this slot (never 0)
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= slotCount) return;
+    const int wave = slotBegin + local;
+    const int n = (wave == 0) ? half : wave;        // wavenumber of this slot (never 0)
+    const int slot = local;                         // table index
     const size_t base = (size_t)(slot / W) * nT * W + (slot % W);
     const float nSq = (float)(n * n);
     const int P = nT / L;
@@ -352,12 +356,14 @@ cudaError_t configureTridiagonal(const GridParams& g, int batch)
     return dispatchTri(g, none, nullptr, batch, nullptr, true, batch, g.nPhi / 2, 0, g.nPhi / 2);
 }
 
-cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream)
+cudaError_t launchBuildSolveTables(const GridParams& g, SpectralTables t, int batch, cudaStream_t stream,
+                                   int slotBegin, int slotCount)
 {
     const TriLaunch l = triLaunch(g, batch);
-    const int half = g.nPhi / 2;
+    if (slotCount < 0) slotCount = g.nPhi / 2;
+    if (slotBegin % l.W || slotCount % l.W) return cudaErrorInvalidValue;
     const int threads = 64;
-    buildSolveTablesKernel<<<(half + threads - 1) / threads, threads, 0, stream>>>(g, t, l.W, l.L);
+    buildSolveTablesKernel<<<(slotCount + threads - 1) / threads, threads, 0, stream>>>(g, t, l.W, l.L, slotBegin, slotCount);
     return cudaGetLastError();
 }
 

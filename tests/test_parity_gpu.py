@@ -654,7 +654,91 @@ def test_cli_restart_from_checkpoint_continues_bit_for_bit(K, tmp_path):
         assert not os.path.exists(str(second / ("%s0.bgeo" % stem)))
 
 
-# ---- theta-band decomposition: virtual ranks on one GPU ----------------------------
+# ---- theta-band decomposition, C++ path (csrc/dist.cu, kamino_dist_*): virtual ranks on one GPU ----------
+
+def _single_gpu_steps(K, nT, steps, scale=1.0):
+    N = 2 * nT
+    rho0 = oa.synthetic_density(nT).reshape(nT, N)
+    with K.KaminoSolver(N, nT, 5.0, 0.005) as s:
+        u0, v0 = s.velPhi.cpuBuffer.copy() * np.float32(scale), s.velTheta.cpuBuffer.copy() * np.float32(scale)
+        set_velocity(s, u0, v0)
+        s.density.cpuBuffer[:] = rho0
+        s.density.copyToGPU()
+        s.stepForward(nSteps=steps)
+        st = state(s)
+        pr = s.pressure.copyBackToCPU().copy()
+    return u0, v0, rho0, st, pr
+
+
+@pytest.mark.parametrize("nT,world", [(128, 4), (256, 2), (512, 8), (128, 1)])
+def test_dist_virtual_ranks_bit_identical_to_single_gpu(K, nT, world):
+    """kamino_dist_*: band-sized buffers, the FFTs writing / reading the transposes' wire layouts, the theta
+    solve on the rank's wavenumber band with band-only LU tables. P virtual ranks on one device
+    (kamino_dist_group_step: device copies where the NCCL ranks send / receive) against kamino_step:
+    u_phi, u_theta, density and pressure bit-identical after 3 steps."""
+    from kaminogpu_b200 import capi, dist
+    u0, v0, rho0, st, pr = _single_gpu_steps(K, nT, 3)
+    grp = dist.LocalGroup(nT, 5.0, 0.005, world)
+    try:
+        grp.upload_global(capi.VEL_PHI, u0)
+        grp.upload_global(capi.VEL_THETA, v0)
+        grp.upload_global(capi.DENSITY, rho0)
+        grp.step(2)
+        grp.step(1)
+        grp.sync()
+        got = {"velPhi": grp.gather(capi.VEL_PHI), "velTheta": grp.gather(capi.VEL_THETA), "density": grp.gather(capi.DENSITY),
+               "pressure": grp.gather(capi.PRESSURE)}
+        held = [r.device_bytes for r in grp.ranks]
+    finally:
+        grp.close()
+    want = dict(st, pressure=pr)
+    for name in ("velPhi", "velTheta", "density", "pressure"):
+        w = words_equal(got[name], want[name])
+        print("dist x%d nTheta %d %-9s identical words %.6f" % (world, nT, name, w))
+        assert np.array_equal(got[name].ravel().view(np.uint32), np.asarray(want[name], np.float32).ravel().view(np.uint32)), name
+    if world > 1:
+        # band-sized memory: a rank holds (rows + 2 x 24 halo) rows of 7 field buffers, 3 spectrum buffers, 1/P of the tables
+        assert max(held) < 0.8 * held[0] * world or world == 2
+
+
+def test_dist_init_velocity_rows_matches_full_field(K):
+    from kaminogpu_b200 import capi, dist
+    nT, world = 128, 4
+    u, v = oa.init_velocity(nT)
+    grp = dist.LocalGroup(nT, 5.0, 0.005, world)
+    try:
+        grp.init_velocity()
+        assert np.array_equal(grp.gather(capi.VEL_PHI).ravel(), u)
+        assert np.array_equal(grp.gather(capi.VEL_THETA).ravel(), v)
+    finally:
+        grp.close()
+
+
+def test_dist_reports_a_backtrace_that_leaves_the_halo(K):
+    """A theta-CFL the 24-row halo cannot cover must not pass silently (r01 ADVICE): the sampler clamps the
+    gather into the resident rows, raises the device flag and kamino_dist_sync returns KAMINO_ERR_STATE."""
+    from kaminogpu_b200 import capi, dist
+    nT, world = 128, 4
+    u, v = oa.init_velocity(nT)
+    grp = dist.LocalGroup(nT, 5.0, 0.005, world)
+    try:
+        grp.upload_global(capi.VEL_PHI, u)
+        grp.upload_global(capi.VEL_THETA, v * np.float32(60.0))         # theta-CFL ~ 40 rows
+        grp.upload_global(capi.DENSITY, oa.synthetic_density(nT))
+        grp.step(1)
+        with pytest.raises(capi.KaminoError) as err:
+            grp.sync()
+        assert err.value.code == capi_err("STATE") and "halo" in str(err.value)
+        # an ordinary run does not trip it
+        grp.upload_global(capi.VEL_PHI, u)
+        grp.upload_global(capi.VEL_THETA, v)
+        grp.step(2)
+        grp.sync()
+    finally:
+        grp.close()
+
+
+# ---- theta-band decomposition, Python prototype + SPIKE research path (banded.py): virtual ranks on one GPU ----
 
 @pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
 def test_banded_step_is_bit_identical_to_single_gpu(K, nT, world):
