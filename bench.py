@@ -14,7 +14,9 @@ N > 1 (launched under torchrun, one rank per GPU): every rank steps its own inde
 simulation of the same shape (ensemble sharding, no data-path collective); `value` is the
 steps of all ranks divided by the slowest rank's time ("scaling": "weak"). The line also
 carries `ensemble_c4`: BASELINE config 4 as written, 64 independent 256 x 512 simulations
-sharded 64/N per rank (strong scaling, simulation-steps/s).
+sharded 64/N per rank (strong scaling, simulation-steps/s), and `banded`: BASELINE config 5, one
+8192 x 16384 simulation theta-band decomposed over the N ranks (C++ step loop with NCCL halo
+exchange and NCCL transposes, kamino_dist_*; ms/step, bytes and GB/s of the transposes).
 
 Timing: W warm-up steps, one untimed K-step call (the same graph chunking as the timed
 call; every step graph is pre-instantiated at context creation), then R repetitions of the
@@ -69,6 +71,9 @@ WORKLOADS = {
     "c4": (256, 0.0, 64, "C4 ensemble of 64 x 256x512, no particles"),
 }
 C4_SIMS = 64
+# BASELINE config 5. The reference cannot run this size; dt <= 0.0025 keeps the equator rows out of the cubic's overflow
+# band and the amplitude of the initial velocity is the one scripts/c5_regime.py found to stay finite.
+C5 = {"nTheta": 8192, "dt": 0.0025, "radius": 5.0, "velocity_scale": 1.0, "steps": 5}
 RADIUS, DT, STEPS_PER_FRAME = 5.0, 0.005, 10
 BYTES_PER_CELL = {"advect": 24, "geometric": 16, "divergence_fft": 12, "tridiagonal": 8, "inverse_fft_gradient": 20}
 KERNELS = ["advect", "geometric", "divergence_fft", "tridiagonal", "inverse_fft_gradient"]
@@ -295,6 +300,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ensemble", action="store_true", help="skip the secondary C4 (64 x 256x512 sharded) measurement")
+    ap.add_argument("--no-banded", action="store_true", help="skip the secondary C5 (8192x16384 theta-band) measurement")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -506,6 +512,58 @@ def main():
                     "ms_per_ensemble_step": esec / K * 1e3, "sims_per_gpu": per_rank,
                     "cell_updates_per_s": K * C4_SIMS / esec * nT4 * 2 * nT4, "reps": len(ereps)}
 
+    # ---- secondary: BASELINE config 5, ONE 8192 x 16384 simulation theta-band decomposed over the N ranks ----------
+    # (kamino_dist_*: C++ step loop, NCCL halo exchange + NCCL transposes around the theta solve; N = 1 runs the same
+    # kernels on one band = the whole grid, so that the N = 1, 2, 4, 8 lines of a scaling run are comparable)
+    banded = None
+    if not args.no_banded and args.workload == "c2":
+        from kaminogpu_b200.dist import DistributedSolver
+        nT5, steps5 = C5["nTheta"], C5["steps"]
+        d = DistributedSolver(nT5, C5["radius"], C5["dt"], device=local_rank)
+        t_init = time.perf_counter()
+        u5, v5 = d.init_velocity()
+        if C5["velocity_scale"] != 1.0:
+            k5 = np.float32(C5["velocity_scale"])
+            d.upload(capi.VEL_PHI, u5 * k5)
+            d.upload(capi.VEL_THETA, v5[:d.rows_of(capi.VEL_THETA)] * k5)
+        jj = (np.arange(d.lo, d.hi, dtype=np.float32) + 0.5) * np.float32(np.pi / nT5)
+        d.upload(capi.DENSITY, np.repeat((0.5 + 0.5 * np.sin(jj) ** 2).astype(np.float32)[:, None], 2 * nT5, axis=1))
+        del u5, v5
+        t_init = time.perf_counter() - t_init
+        ext = torch.cuda.ExternalStream(d.cuda_stream)
+        d.step(3)
+        d.sync()
+        breps = []
+        for _ in range(3):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ext)
+            d.step(steps5)
+            b.record(ext)
+            d.sync()
+            barrier()
+            breps.append(a.elapsed_time(b) * 1e-3)
+        breps = max_over_ranks(breps)
+        d.comm_stats(enable=1)
+        d.step(steps5)
+        d.sync()
+        cs = d.comm_stats(enable=0)
+        back = d.download(capi.VEL_PHI)
+        fin5 = max_over_ranks([0.0 if np.isfinite(back).all() else 1.0])[0] == 0.0
+        tsec = max_over_ranks([cs["transpose_s"] / max(cs["steps"], 1), cs["halo_s"] / max(cs["steps"], 1)])
+        mem = max_over_ranks([float(d.device_bytes)])[0]
+        d.close()
+        bsec = statistics.median(breps) / steps5
+        banded = {"workload": "C5: one %dx%d simulation, theta-band decomposed over %d GPU%s" % (nT5, 2 * nT5, world, "s" if world > 1 else ""),
+                  "ms_per_step": bsec * 1e3, "steps_per_s": 1.0 / bsec, "cell_updates_per_s": nT5 * 2 * nT5 / bsec, "scaling": "strong",
+                  "steps": steps5, "reps": len(breps), "finite": fin5, "dt": C5["dt"], "radius": C5["radius"],
+                  "velocity_scale": C5["velocity_scale"], "device_gb_per_rank": mem / 1e9, "init_s": t_init,
+                  "collectives": "none (one band)" if world == 1 else "NCCL send/recv: 24-row halos + two transposes of the half spectrum per step",
+                  "transpose_bytes_sent_per_rank_per_step": cs["transpose_bytes_per_step"],
+                  "halo_bytes_sent_per_rank_per_step": cs["halo_bytes_per_step"],
+                  "transpose_ms_per_step": tsec[0] * 1e3, "halo_ms_per_step": tsec[1] * 1e3,
+                  "transpose_gbs_per_rank": (cs["transpose_bytes_per_step"] / tsec[0] / 1e9) if world > 1 and tsec[0] > 0 else None}
+
     if rank == 0:
         sims = batch * world
         value = K * sims / seconds
@@ -563,6 +621,8 @@ def main():
             res["warning"] = "cold step faster than the warm median: timing defect?"
         if ensemble is not None:
             res["ensemble_c4"] = ensemble
+        if banded is not None:
+            res["banded"] = banded
         if not args.no_cpu_baseline and world == 1:
             res["cpu_baseline"] = cpu_baseline(nTheta, pdens)
         print(json.dumps(res))

@@ -88,7 +88,7 @@ class DistributedSolver(_Rank):
     def __init__(self, nTheta, radius, dt, device=0):
         import torch
         import torch.distributed as dist
-        rank, world = dist.get_rank(), dist.get_world_size()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
         lib = capi.load()
         ident = (ctypes.c_ubyte * 128)()
         if world > 1:
@@ -134,8 +134,15 @@ class LocalGroup:
         _check(capi.load().kamino_dist_group_step(self._handles, self.world, nSteps), self.ranks[0].handle)
 
     def sync(self):
+        """Synchronise every rank (each clears its own halo-violation flag), then raise the first error."""
+        first = None
         for r in self.ranks:
-            r.sync()
+            try:
+                r.sync()
+            except capi.KaminoError as e:
+                first = first or e
+        if first is not None:
+            raise first
 
     def gather(self, field):
         return np.concatenate([r.download(field) for r in self.ranks], axis=0)

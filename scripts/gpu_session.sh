@@ -30,9 +30,9 @@ PY
 if [ -n "$NCU" ]; then
   # launch list (cold-cache, serialised: shares only) and one full capture of the five kernels of a step
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 32 -c 50 --csv --log-file $OUT/launches.csv \
-      python bench.py --steps 20 --warmup 3 --reps 1 --no-ensemble --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
+      python bench.py --steps 20 --warmup 3 --reps 1 --no-ensemble --no-banded --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -s 32 -c 5 -o $OUT/prof_c2 -f \
-      python bench.py --steps 20 --warmup 3 --reps 1 --no-ensemble --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+      python bench.py --steps 20 --warmup 3 --reps 1 --no-ensemble --no-banded --no-cpu-baseline > $OUT/ncu_full.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -s 32 -c 5 -o $OUT/prof_c3 -f \
       python bench.py --workload c3 --steps 20 --warmup 3 --reps 1 --no-cpu-baseline > $OUT/ncu_full_c3.log 2>&1
 fi
