@@ -2,7 +2,7 @@
 """bench.py -- steps/s and cell-updates/s of the per-timestep solver path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--reps R]
-                    [--impl b200|reference|cli] [--workload c2|c1|c3|c4|c4shard]
+                    [--impl b200|reference|cli] [--workload c2|c1|c3|c4|c5]
 
 Workload (BASELINE.json configs[1], "C2"): one 512 x 1024 (theta x phi) simulation with
 density advection and 1,048,352 passive tracer particles (particleDensity = 2, the closest
@@ -69,6 +69,7 @@ WORKLOADS = {
     "c2": (512, 2.0, 1, "C2 512x1024 + 1,048,352 particles"),
     "c3": (2048, 0.0, 1, "C3 2048x4096, no particles"),
     "c4": (256, 0.0, 64, "C4 ensemble of 64 x 256x512, no particles"),
+    "c5": (8192, 0.0, 1, "C5 8192x16384 on ONE GPU, no particles, dt 0.0025"),
 }
 C4_SIMS = 64
 # BASELINE config 5. The reference cannot run this size; dt <= 0.0025 keeps the equator rows out of the cubic's overflow
@@ -372,7 +373,8 @@ def main():
         def __exit__(self, *exc):
             return False
 
-    s = KaminoSolver(nPhi, nTheta, RADIUS, DT, device=local_rank, batch=batch)
+    dt_run = C5["dt"] if args.workload == "c5" else DT
+    s = KaminoSolver(nPhi, nTheta, RADIUS, dt_run, device=local_rank, batch=batch)
     s.set_stream(stream.cuda_stream)           # so that torch.cuda.Event brackets our launches
     rho0 = synthetic_density(nTheta)
     for sim in range(batch):
@@ -590,7 +592,7 @@ def main():
                      "ms_per_step_min": min(reps) / K * 1e3, "ms_per_step_max": max(reps) / K * 1e3},
             "cell_updates_per_s": value * cells * batch,
             "config": {"workload": desc + (" per GPU" if world > 1 else ""), "nTheta": nTheta, "nPhi": nPhi,
-                       "particles": nPart, "batch_per_gpu": batch, "dt": DT, "radius": RADIUS,
+                       "particles": nPart, "batch_per_gpu": batch, "dt": dt_run, "radius": RADIUS,
                        "parallelism": "ensemble x%d (independent simulations, no collective)" % world if world > 1 else "single simulation",
                        "l2": "state (%.0f MB) is smaller than the 126 MB L2: consecutive steps of one simulation run "
                              "L2-resident by nature, so `value` is NOT flushed; `cold` flushes L2 (512 MB write) before every step"

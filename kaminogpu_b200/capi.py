@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkamino_b200.so")
+# KAMINO_B200_LIB: development aid of this binding (A/B runs of alternative builds of the library), not read by the library
+LIB_PATH = os.environ.get("KAMINO_B200_LIB") or os.path.join(_HERE, "libkamino_b200.so")
 
 # field ids (include/kamino_b200.h)
 VEL_PHI, VEL_THETA, DENSITY, PRESSURE = 0, 1, 2, 3

@@ -77,8 +77,13 @@ __device__ __forceinline__ float backtraceFast(const SamplerRegs& g, float cofTh
     const float gPhi = __fmul_rn(__fadd_rn((float)i, offPhi), g.h);
     const float gTheta = __fmul_rn(__fadd_rn((float)j, offTheta), g.h);
     bad = false;
-    PendingSample pu = sampleIssueFast<kVPhi>(g, gPhi, gTheta, tilePhi, bad);
-    PendingSample pv = sampleIssueFast<kVTheta>(g, gPhi, gTheta, tileTheta, bad);
+#ifdef KB_STAGE1_CHECK
+    constexpr bool kNodeCheck = true;
+#else
+    constexpr bool kNodeCheck = false;
+#endif
+    PendingSample pu = sampleIssueFast<kVPhi, kNodeCheck>(g, gPhi, gTheta, tilePhi, bad);       // at the cell's own node
+    PendingSample pv = sampleIssueFast<kVTheta, kNodeCheck>(g, gPhi, gTheta, tileTheta, bad);
     const float guPhi = sampleFinish(pu);
     const float guTheta = sampleFinish(pv);
     const float deltaPhi = __fmul_rn(guPhi, cofPhi);
@@ -215,22 +220,23 @@ advectKernel(GridParams g, AdvectArgs a)
                                                              cofCentred, tPhi, tTheta, tRho);
         return;
     }
-    long k;
+    unsigned k;                                     // particle counts are far below 2^32
     if (a.latticeInner > 0) {
-        // compact patch of the particle lattice per warp / block (see AdvectArgs)
-        const int pb = particleBlock;
-        const int blockO = pb / a.blocksInner, blockI = pb - blockO * a.blocksInner;
-        const int log2BI = a.log2Inner < 4 ? 4 : a.log2Inner;               // block patch: 2^log2BI rows
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int warpsInner = 1 << (log2BI - a.log2Inner);
-        const int wi = warp & (warpsInner - 1), wo = warp >> (log2BI - a.log2Inner);
-        const int inner = (blockI << log2BI) + (wi << a.log2Inner) + (lane & ((1 << a.log2Inner) - 1));
-        const int outer = blockO * (kAdvectThreads >> log2BI) + wo * (32 >> a.log2Inner) + (lane >> a.log2Inner);
-        k = (inner < a.latticeInner && outer < a.latticeOuter) ? (long)outer * a.latticeInner + inner : g.numParticles;
+        // compact patch of the particle lattice per warp / block (see AdvectArgs); pb / blocksInner by a multiply
+        // with ceil(2^32 / blocksInner) (exact: pb * blocksInner < 2^32; magic 0 stands for a divisor of 1)
+        const unsigned pb = (unsigned)particleBlock;
+        const unsigned blockO = a.innerMagic ? __umulhi(pb, a.innerMagic) : pb, blockI = pb - blockO * a.blocksInner;
+        const unsigned log2BI = a.log2Inner < 4 ? 4 : a.log2Inner;          // block patch: 2^log2BI rows
+        const unsigned sh = log2BI - a.log2Inner;
+        const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const unsigned wi = warp & ((1u << sh) - 1), wo = warp >> sh;
+        const unsigned inner = (blockI << log2BI) + (wi << a.log2Inner) + (lane & ((1u << a.log2Inner) - 1));
+        const unsigned outer = blockO * (kAdvectThreads >> log2BI) + wo * (32u >> a.log2Inner) + (lane >> a.log2Inner);
+        k = (inner < (unsigned)a.latticeInner && outer < (unsigned)a.latticeOuter) ? outer * a.latticeInner + inner : 0xffffffffu;
     } else {
-        k = (long)particleBlock * kAdvectThreads + threadIdx.x;
+        k = (unsigned)particleBlock * kAdvectThreads + threadIdx.x;
     }
-    if (k < g.numParticles) {                       // the reference has no tail guard (:323)
+    if (k < (unsigned long)g.numParticles) {        // the reference has no tail guard (:323)
         const float2* in = reinterpret_cast<const float2*>(a.particles) + (size_t)sim * g.numParticles;
         float2* out = reinterpret_cast<float2*>(a.particlesOut) + (size_t)sim * g.numParticles;
         out[k] = pushParticle(sr, a.consts, g.radius, g.dt, g.cofTheta, velPhi, velTheta, in[k]);
@@ -281,7 +287,7 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
     a.tileBlocks = (g.nPhi / 32) * (g.rowCount / kTileRows);      // rowBegin, rowCount: multiples of kTileRows
     int blocksParticles = (a.particles && g.numParticles > 0)
         ? (int)((g.numParticles + kAdvectThreads - 1) / kAdvectThreads) : 0;
-    a.latticeInner = a.latticeOuter = a.log2Inner = a.blocksInner = 0;
+    a.latticeInner = a.latticeOuter = a.log2Inner = a.blocksInner = 0; a.innerMagic = 0;
     if (blocksParticles > 0) {
         // numOfParticles = numTheta * (2 numTheta) for a seeded set (kernel/KaminoParticles.cu:22-25)
         const long m = (long)(sqrt((double)g.numParticles / 2.0) + 0.5);
@@ -293,6 +299,7 @@ cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStrea
             if (log2Inner < 5) {       // a 32-row patch is the linear mapping (dense particle sets, r01g A/B at C1)
                 a.latticeInner = (int)m; a.latticeOuter = (int)(2 * m); a.log2Inner = log2Inner;
                 a.blocksInner = (int)((m + (1 << log2BI) - 1) >> log2BI);
+                a.innerMagic = a.blocksInner > 1 ? (unsigned)(((1ull << 32) + a.blocksInner - 1) / a.blocksInner) : 0u;   // 0: divisor 1
                 const int rowsOuter = kAdvectThreads >> log2BI;
                 blocksParticles = a.blocksInner * (int)((2 * m + rowsOuter - 1) / rowsOuter);
             }

@@ -383,7 +383,11 @@ int kamino_dist_create(kamino_dist** out, int device, int nTheta, float radius, 
     d->arenaBytes = 7 * fieldBytes + sendBytes + packedBytes + backBytes + tableBytes;
     cudaError_t e = cudaMalloc((void**)&d->arena, d->arenaBytes);
     if (e != cudaSuccess) { int rc = fail(nullptr, (int)e, "cudaMalloc(band arena)"); delete d; return rc; }
+    // cudaMemset on the legacy stream is asynchronous for device memory and does NOT order against the non-blocking
+    // stream the table builders run on: wait for it (at 8192 x 16384 the 3 GB clear otherwise overtakes the builders
+    // and zeroes the first rows of the tables they have just written)
     cudaMemset(d->arena, 0, d->arenaBytes);
+    cudaDeviceSynchronize();
     char* p = d->arena;
     auto take = [&p](size_t bytes) { char* r = p; p += alignUp(bytes, 256); return r; };
     const ptrdiff_t shift = (ptrdiff_t)d->memLo * (ptrdiff_t)N;      // virtual base: global row indexing

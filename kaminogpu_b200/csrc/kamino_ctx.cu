@@ -306,6 +306,7 @@ int allocParticles(kamino_ctx* ctx, long n)
     const size_t snapshotBytes = alignUp(sizeof(float) * ctx->snapshotFloats, 256);
     KB_TRY(ctx, cudaMalloc((void**)&ctx->particleArena, particleBytes * 2 + snapshotBytes));
     KB_TRY(ctx, cudaMemset(ctx->particleArena, 0, particleBytes * 2 + snapshotBytes));
+    KB_TRY(ctx, cudaDeviceSynchronize());          // see the arena clear in kamino_create
     ctx->particles[0] = (float*)ctx->particleArena;
     ctx->particles[1] = (float*)(ctx->particleArena + particleBytes);
     ctx->snapshot = (float*)(ctx->particleArena + 2 * particleBytes);
@@ -367,7 +368,12 @@ int kamino_create(kamino_ctx** out, int device, int nTheta, float radius, float 
     ctx->arenaBytes = fieldBytes * (4 + 2 * ctx->velBuffers) + tableBytes;   // 2 x (u_phi, u_theta), 2 x density, pressure, spectrum
     e = cudaMalloc((void**)&ctx->arena, ctx->arenaBytes);
     if (e != cudaSuccess) { int rc = fail(nullptr, (int)e, "cudaMalloc(arena)"); delete ctx; return rc; }
+    // cudaMemset on the legacy stream is asynchronous for device memory and does NOT order against the non-blocking
+    // streams of this context: wait for it. (Found at 8192 x 16384, r02f: the 6 GB clear was still running when the
+    // table builders started on ownStream and zeroed the first ~60 rows of the LU tables after they had been written;
+    // the step was finite but not repeatable. This also explains the non-finite banded run of r01o.)
     cudaMemset(ctx->arena, 0, ctx->arenaBytes);
+    cudaDeviceSynchronize();
     char* p = ctx->arena;
     auto take = [&p](size_t bytes) { char* r = p; p += bytes; return r; };
     for (int k = 0; k < ctx->velBuffers; ++k) ctx->velPhi[k] = (float*)take(fieldBytes);

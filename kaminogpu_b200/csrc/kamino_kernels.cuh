@@ -32,6 +32,7 @@ struct AdvectArgs {
     int latticeInner, latticeOuter;              // numTheta, numPhi of the lattice (0: linear mapping)
     int log2Inner;                               // log2 of the warp patch height (rows of the lattice)
     int blocksInner;                             // particle blocks along the inner (theta) dimension
+    unsigned innerMagic;                         // ceil(2^32 / blocksInner): division by a multiply
 };
 
 cudaError_t launchAdvect(const GridParams& g, AdvectArgs a, int batch, cudaStream_t stream);

@@ -325,7 +325,11 @@ __device__ __forceinline__ PendingSample sampleIssueTiled(const SamplerRegs& g, 
 // so the values of unflagged lanes are exactly those of the branching form; what goes away is
 // the divergence bookkeeping around every sample (two branches, BSSY, BSYNC) and, with the call
 // to the out-of-line general path gone from the hot loop, the register spills around it.
-template <int KIND>
+// CHECK = false: the sample sits at a node of one of the block's own cells (first stage of a backtrace). Its
+// cell index is within one of the node's own (the coordinate is a product of an integer or half-integer and h,
+// rounded a few times: |normed - exact| < 0.01 up to index 16384), i.e. at least one row and three columns inside
+// the tile's halo, so neither the test nor the clamp is needed.
+template <int KIND, bool CHECK = true>
 __device__ __forceinline__ PendingSample sampleIssueFast(const SamplerRegs& g, float phiRaw, float thetaRaw,
                                                          unsigned tile, bool& bad)
 {
@@ -337,9 +341,10 @@ __device__ __forceinline__ PendingSample sampleIssueFast(const SamplerRegs& g, f
     const int thetaIndex = (int)floorf(normedTheta);
     const int tr = thetaIndex - g.tileRow0;
     const int tc = phiIndex - g.tileCol0;
-    bad = bad || (unsigned)tr >= (unsigned)(kTileH - 1) || (unsigned)tc >= (unsigned)(kTileW - 1);
+    if (CHECK) bad = bad || (unsigned)tr >= (unsigned)(kTileH - 1) || (unsigned)tc >= (unsigned)(kTileW - 1);
     // valid lanes: tr * kTileStride + tc <= (kTileH - 2) * kTileStride + kTileW - 2, never altered by the clamp
-    const unsigned cellIndex = min((unsigned)(tr * kTileStride + tc), (unsigned)((kTileH - 2) * kTileStride + kTileW - 2));
+    const unsigned cellIndex = CHECK ? min((unsigned)(tr * kTileStride + tc), (unsigned)((kTileH - 2) * kTileStride + kTileW - 2))
+                                     : (unsigned)(tr * kTileStride + tc);
     PendingSample p;
     p.alphaPhi = __fsub_rn(normedPhi, (float)phiIndex);
     p.alphaTheta = __fsub_rn(normedTheta, (float)thetaIndex);
