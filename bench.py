@@ -463,12 +463,16 @@ def main():
             e1.record(stream)
             stream.synchronize()
             return reps_ * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
-        l2_gbs = 2.0 * copy_gbs(16 << 20, 200)           # 16 MB -> 16 MB, both L2-resident: read + write bytes
+        l2_gbs = 2.0 * max(copy_gbs(16 << 20, 200) for _ in range(3))   # 16 MB -> 16 MB, both L2-resident: read + write bytes, best of 3
         host_buf = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
         dev_buf = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        barrier()                                        # all ranks copy at the same time: the host side is shared
         d2h_gbs = copy_gbs(64 << 20, 5, src=dev_buf, dst=host_buf)
+        barrier()
         h2d_gbs = copy_gbs(64 << 20, 5, src=host_buf, dst=dev_buf)
         del host_buf, dev_buf
+        d2h_gbs = -max_over_ranks([-d2h_gbs])[0]         # slowest rank
+        h2d_gbs = -max_over_ranks([-h2d_gbs])[0]
 
         # ---- end to end: upload + frames of STEPS_PER_FRAME steps + read-backs --------------
         frames = max(K // STEPS_PER_FRAME, 1)
@@ -605,6 +609,7 @@ def main():
                     "h2d_bytes_per_step": state_bytes / e2e_steps, "d2h_bytes_per_step": frame_bytes / STEPS_PER_FRAME,
                     "steps_per_frame": STEPS_PER_FRAME, "frames": frames, "reps": len(e2e_reps),
                     "pcie_d2h_gbs": d2h_gbs, "pcie_h2d_gbs": h2d_gbs,
+                    "pcie_note": "64 MB pinned copies, all %d ranks at the same time, slowest rank" % world,
                     "d2h_floor_ms_per_step": frame_bytes / STEPS_PER_FRAME / (d2h_gbs * 1e9) * 1e3},
             "cold": {"value": sims / cold_s, "unit": "steps/s", "ms_per_step": cold_s * 1e3, "steps": ncold},
             "gpu_launches": nlaunch * K,

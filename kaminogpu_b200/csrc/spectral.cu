@@ -38,29 +38,52 @@ namespace {
 // Every thread of the block must call this (it contains __syncthreads()).
 // `tw` is the twiddle table (global, or its shared-memory copy once `twReady` has completed:
 // the first pass needs no twiddles, so the wait sits after it).
-template <int SIGN>
+// LOG2N > 0: the transform length is a compile-time constant (the BASELINE sizes), so T, the pass sizes Ns and the
+// padded shared-memory offsets of the scatters / gathers fold into immediates: in the runtime-N build 34 % of the
+// executed instructions of the FFT kernels were IADD3 / LEA / SHF address arithmetic (r02j SASS profile).
+// LOG2N == 0: any power of two >= 32, sizes read from the arguments. Same arithmetic either way.
+template <int SIGN, int LOG2N>
 __device__ __forceinline__ void fftFromRegisters(float2* v, float2* buf, int t, int T, int N, int log2N,
                                                  const float2* tw, uint64_t* twReady)
 {
     using namespace fft;
-    int Ns;
-    switch (log2N & 3) {
-    case 1: passCompute<SIGN, 2>(v, t, T, N, 1, tw); passScatter<2>(v, buf, t, T, 1); Ns = 2; break;
-    case 2: passCompute<SIGN, 4>(v, t, T, N, 1, tw); passScatter<4>(v, buf, t, T, 1); Ns = 4; break;
-    case 3: passCompute<SIGN, 8>(v, t, T, N, 1, tw); passScatter<8>(v, buf, t, T, 1); Ns = 8; break;
-    default: passCompute<SIGN, 16>(v, t, T, N, 1, tw); passScatter<16>(v, buf, t, T, 1); Ns = 16; break;
-    }
-    if (twReady) tma::mbarWait(twReady, 0);
-    __syncthreads();
-    const float2* twPass = tw;                 // packed per-pass tables, fft_core.cuh
-    while (Ns < N) {
-        passGather(v, buf, t, T);
-        __syncthreads();                       // everyone has read before anyone overwrites
-        passCompute<SIGN, 16>(v, t, T, N, Ns, twPass);
-        passScatter<16>(v, buf, t, T, Ns);
-        twPass += 15 * Ns;
-        Ns <<= 4;
+    if constexpr (LOG2N != 0) {
+        constexpr int kN = 1 << LOG2N, kT = kN >> 4;
+        constexpr int kFirst = (LOG2N & 3) ? (1 << (LOG2N & 3)) : 16;
+        passCompute<SIGN, kFirst>(v, t, kT, kN, 1, tw);
+        passScatter<kFirst>(v, buf, t, kT, 1);
+        if (twReady) tma::mbarWait(twReady, 0);
         __syncthreads();
+        const float2* twPass = tw;                 // packed per-pass tables, fft_core.cuh
+#pragma unroll
+        for (int Ns = kFirst; Ns < kN; Ns <<= 4) {
+            passGather(v, buf, t, kT);
+            __syncthreads();                       // everyone has read before anyone overwrites
+            passCompute<SIGN, 16>(v, t, kT, kN, Ns, twPass);
+            passScatter<16>(v, buf, t, kT, Ns);
+            twPass += 15 * Ns;
+            __syncthreads();
+        }
+    } else {
+        int Ns;
+        switch (log2N & 3) {
+        case 1: passCompute<SIGN, 2>(v, t, T, N, 1, tw); passScatter<2>(v, buf, t, T, 1); Ns = 2; break;
+        case 2: passCompute<SIGN, 4>(v, t, T, N, 1, tw); passScatter<4>(v, buf, t, T, 1); Ns = 4; break;
+        case 3: passCompute<SIGN, 8>(v, t, T, N, 1, tw); passScatter<8>(v, buf, t, T, 1); Ns = 8; break;
+        default: passCompute<SIGN, 16>(v, t, T, N, 1, tw); passScatter<16>(v, buf, t, T, 1); Ns = 16; break;
+        }
+        if (twReady) tma::mbarWait(twReady, 0);
+        __syncthreads();
+        const float2* twPass = tw;                 // packed per-pass tables, fft_core.cuh
+        while (Ns < N) {
+            passGather(v, buf, t, T);
+            __syncthreads();                       // everyone has read before anyone overwrites
+            passCompute<SIGN, 16>(v, t, T, N, Ns, twPass);
+            passScatter<16>(v, buf, t, T, Ns);
+            twPass += 15 * Ns;
+            Ns <<= 4;
+            __syncthreads();
+        }
     }
 }
 
@@ -144,14 +167,15 @@ __device__ __forceinline__ uint64_t* stageTwiddles(const float2* __restrict__ tw
 // Each transform handles a pair of theta rows (z = div_j + i div_{j+1}) with T = N/16 threads;
 // a block of BLOCK threads holds BLOCK/T transforms. grid (ceil(nTheta/2 / (BLOCK/T)), batch),
 // dynamic smem: [twiddles N float2 if STAGE] + (BLOCK/T) * paddedSize(N) float2.
-template <int BLOCK, bool STAGE, int MINB, bool PACKED>
-__global__ void __launch_bounds__(BLOCK, MINB)
+template <int BLOCK, bool STAGE, int LOG2N, bool PACKED>
+__global__ void __launch_bounds__(BLOCK)
 divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ velPhiAll,
                     const float* __restrict__ velThetaAll, float2* __restrict__ spectrumAll, SpectrumLayout lay)
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
-    const int N = g.nPhi, half = N >> 1, log2T = g.log2NPhi - 4, T = 1 << log2T;
+    const int log2N = LOG2N ? LOG2N : g.log2NPhi;
+    const int N = 1 << log2N, half = N >> 1, log2T = log2N - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
     const int pairs = (g.rowBegin + g.rowCount) >> 1;             // one past the last pair of the band
     const int pairRaw = (g.rowBegin >> 1) + blockIdx.x * (BLOCK >> log2T) + local;
@@ -164,7 +188,7 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
     const float* velTheta = velThetaAll + (size_t)sim * g.cells;
     float2* spectrum = spectrumAll + (size_t)sim * (g.cells >> 1);
 
-    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, g.log2NPhi));
+    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, log2N));
     const float2* tw = STAGE ? twShared : t.twiddle;
     pdlWait();                                   // the velocity comes from the previous kernel
 
@@ -201,7 +225,7 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
                                        __fmaf_rn(facB, __fsub_rn(b1[e], b0[e]), termB));
         }
     }
-    fftFromRegisters<-1>(v, buf, tt, T, N, g.log2NPhi, tw, twReady);
+    fftFromRegisters<-1, LOG2N>(v, buf, tt, T, N, log2N, tw, twReady);
 
     // v[m] = Z[tt + m*T]. Separate the two real rows and scale by 1/N (shiftFKernel,
     // kernel/KaminoCore.cu:652-653); only k = 1 .. N/2 is kept, the Nyquist mode in slot 0.
@@ -231,15 +255,16 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
 
 // One transform per theta row with T = N/16 threads, BLOCK/T rows per block.
 // grid (ceil(nTheta / (BLOCK/T)), batch), dynamic smem as for the forward kernel.
-template <int BLOCK, bool STAGE, int MINB, bool PACKED>
-__global__ void __launch_bounds__(BLOCK, MINB)
+template <int BLOCK, bool STAGE, int LOG2N, bool PACKED>
+__global__ void __launch_bounds__(BLOCK)
 inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restrict__ spectrumAll,
                          float* __restrict__ velPhiAll, float* __restrict__ velThetaAll,
                          float* __restrict__ pressureAll, SpectrumLayout lay)
 {
     extern __shared__ __align__(16) float2 smem[];
     __shared__ __align__(8) uint64_t twBar;
-    const int N = g.nPhi, half = N >> 1, nT = g.nTheta, log2T = g.log2NPhi - 4, T = 1 << log2T;
+    const int log2N = LOG2N ? LOG2N : g.log2NPhi;
+    const int N = 1 << log2N, half = N >> 1, nT = g.nTheta, log2T = log2N - 4, T = 1 << log2T;
     const int local = threadIdx.x >> log2T, tt = threadIdx.x & (T - 1);
     const int rowEnd = g.rowBegin + g.rowCount;
     const int rowRaw = g.rowBegin + blockIdx.x * (BLOCK >> log2T) + local;
@@ -255,7 +280,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
     const float2* rowU = PACKED ? spectrum + (size_t)(j - lay.rowBase) * lay.rowPitch : spectrum + (size_t)j * half;
     const float2* rowS = hasSouth ? rowU + (PACKED ? lay.rowPitch : half) : rowU;     // !hasSouth: Y = 0
 
-    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, g.log2NPhi));
+    uint64_t* twReady = stageTwiddles<STAGE>(t.twiddle, twShared, &twBar, fft::twiddleTableSize(N, log2N));
     const float2* tw = STAGE ? twShared : t.twiddle;
     pdlWait();                                   // the spectrum comes from the previous kernel
 
@@ -263,6 +288,31 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
     // Thread tt needs W at idx = tt + e*T: for idx < N/2 from slot idx, for idx > N/2 from the
     // mirrored slot N - idx, for idx = N/2 from slot 0 (the Nyquist mode, real parts only).
     float2 v[16];
+    // N = 4096 (256-thread blocks, 80 registers, three blocks per SM): all 32 loads of the two rows are issued before
+    // any is used, and so are the 32 loads of the old velocity in the epilogue -- one exposed memory latency each
+    // instead of two; together with the twiddles read through L1 instead of a 32 KB shared-memory copy per block
+    // (r02m A/B at 2048 x 4096: 48.1 us against 55.2; either change alone is a loss: 57.3 / 53.3 us; the forward
+    // kernel keeps its staged twiddles: 45.0 us without them against 37.9). The 1024-thread blocks of N = 16384 have no
+    // registers to spare (972 vs 965 us), the 64-thread blocks of N <= 1024 are launch-latency-bound either way.
+    constexpr bool kOneLatency = (BLOCK == 256);
+    if constexpr (kOneLatency) {
+        float2 x[16], sth[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int idx = tt + (e << log2T);
+            const int slot = (e < 8) ? idx : ((N - idx) & (half - 1));     // idx = N/2 -> 0
+            const size_t at = PACKED ? (size_t)(slot >> lay.log2Block) * lay.blockPitch + (slot & ((1 << lay.log2Block) - 1)) : (size_t)slot;
+            x[e] = __ldg(rowU + at);
+            sth[e] = __ldg(rowS + at);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int idx = tt + (e << log2T);
+            const float2 y = make_float2(sth[e].x - x[e].x, sth[e].y - x[e].y);
+            if (e < 8) v[e] = (idx == 0) ? make_float2(0.0f, 0.0f) : make_float2(x[e].x - y.y, x[e].y + y.x);
+            else v[e] = (idx == half) ? make_float2(x[e].x, y.x) : make_float2(x[e].x + y.y, y.x - x[e].y);
+        }
+    } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float2 x[8], sth[8];
@@ -282,7 +332,8 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
             else v[8 + e] = (idx == half) ? make_float2(x[e].x, y.x) : make_float2(x[e].x + y.y, y.x - x[e].y);
         }
     }
-    fftFromRegisters<+1>(v, buf, tt, T, N, g.log2NPhi, tw, twReady);
+    }
+    fftFromRegisters<+1, LOG2N>(v, buf, tt, T, N, log2N, tw, twReady);
 
     // v[m] = z[i], i = tt + m*T: z.x = p[j][i], z.y = p[j+1][i] - p[j][i]
     if (!valid) return;
@@ -292,6 +343,24 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
     const float invDenomPhi = 1.0f / __ldg(t.gradPhiDenom + j);
     const float invNegH = -1.0f / g.h;
     float* pressure = pressureAll ? pressureAll + (size_t)sim * g.cells + (size_t)j * N : nullptr;
+    if constexpr (kOneLatency) {
+        float uOld[16], vOld[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int i = tt + (m << log2T);
+            uOld[m] = velPhi[i];
+            vOld[m] = hasSouth ? velTheta[i] : 0.0f;
+        }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int i = tt + (m << log2T);
+            const float2 zi = v[m];
+            const float pWest = buf[fft::pad((i - 1) & (N - 1))].x;
+            velPhi[i] = __fmaf_rn(__fsub_rn(zi.x, pWest), invDenomPhi, uOld[m]);
+            if (hasSouth) velTheta[i] = __fmaf_rn(zi.y, invNegH, vOld[m]);
+            if (pressure) pressure[i] = zi.x;
+        }
+    } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float uOld[8], vOld[8];
@@ -310,6 +379,7 @@ inverseFFTGradientKernel(GridParams g, SpectralTables t, const float2* __restric
             if (hasSouth) velTheta[i] = __fmaf_rn(zi.y, invNegH, vOld[m]);
             if (pressure) pressure[i] = zi.x;
         }
+    }
     }
 }
 
@@ -344,39 +414,42 @@ FftLaunch fftLaunch(const GridParams& g)
     return l;
 }
 
-template <int BLOCK, bool STAGE, int MINB, bool PACKED>
+template <int BLOCK, bool STAGE, int LOG2N, bool PACKED>
 cudaError_t fftDispatchLayout(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
                               const float* velPhiIn, const float* velThetaIn, float2* spectrum,
                               float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream, const SpectrumLayout& lay)
 {
+    // the inverse kernel of N = 4096 reads its twiddles through L1 (see the kernel)
+    constexpr bool kStageInverse = STAGE && BLOCK != 256;
+    const size_t smemInverse = l.smem - ((STAGE && !kStageInverse) ? sizeof(float2) * (size_t)g.nPhi : 0);
     if (which == 0) {           // configure
-        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE, MINB, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        cudaError_t e = cudaFuncSetAttribute(divergenceFFTKernel<BLOCK, STAGE, LOG2N, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, STAGE, MINB, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        return cudaFuncSetAttribute(inverseFFTGradientKernel<BLOCK, kStageInverse, LOG2N, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemInverse);
     }
     if (which == 1) {
         const int pairs = g.rowCount / 2;
         dim3 grid((pairs + l.perBlock - 1) / l.perBlock, batch);
-        return launchChained(divergenceFFTKernel<BLOCK, STAGE, MINB, PACKED>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum, lay);
+        return launchChained(divergenceFFTKernel<BLOCK, STAGE, LOG2N, PACKED>, grid, dim3(BLOCK), l.smem, stream, g, t, velPhiIn, velThetaIn, spectrum, lay);
     } else {
         dim3 grid((g.rowCount + l.perBlock - 1) / l.perBlock, batch);
-        return launchChained(inverseFFTGradientKernel<BLOCK, STAGE, MINB, PACKED>, grid, dim3(BLOCK), l.smem, stream, g, t,
+        return launchChained(inverseFFTGradientKernel<BLOCK, kStageInverse, LOG2N, PACKED>, grid, dim3(BLOCK), smemInverse, stream, g, t,
                              (const float2*)spectrum, velPhi, velTheta, pressure, lay);
     }
 }
 
-template <int BLOCK, bool STAGE, int MINB>
+template <int BLOCK, bool STAGE, int LOG2N>
 cudaError_t fftDispatch(int which, const GridParams& g, const SpectralTables& t, const FftLaunch& l,
                         const float* velPhiIn, const float* velThetaIn, float2* spectrum,
                         float* velPhi, float* velTheta, float* pressure, int batch, cudaStream_t stream, const SpectrumLayout* lay)
 {
     if (which == 0) {           // configure both addressing variants
-        cudaError_t e = fftDispatchLayout<BLOCK, STAGE, MINB, false>(0, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
+        cudaError_t e = fftDispatchLayout<BLOCK, STAGE, LOG2N, false>(0, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
         if (e != cudaSuccess) return e;
-        return fftDispatchLayout<BLOCK, STAGE, MINB, true>(0, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
+        return fftDispatchLayout<BLOCK, STAGE, LOG2N, true>(0, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
     }
-    if (lay) return fftDispatchLayout<BLOCK, STAGE, MINB, true>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, *lay);
-    return fftDispatchLayout<BLOCK, STAGE, MINB, false>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
+    if (lay) return fftDispatchLayout<BLOCK, STAGE, LOG2N, true>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, *lay);
+    return fftDispatchLayout<BLOCK, STAGE, LOG2N, false>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, SpectrumLayout{});
 }
 
 cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, const float* velPhiIn,
@@ -384,15 +457,20 @@ cudaError_t fftSelect(int which, const GridParams& g, const SpectralTables& t, c
                       float* pressure, int batch, cudaStream_t stream, const SpectrumLayout* lay = nullptr)
 {
     const FftLaunch l = fftLaunch(g);
-#define KB_FFT(B, S) return fftDispatch<B, S, 0>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, lay)
+#define KB_FFT(B, S, L2N) return fftDispatch<B, S, L2N>(which, g, t, l, velPhiIn, velThetaIn, spectrum, velPhi, velTheta, pressure, batch, stream, lay)
+    // blocks of 128 threads and more hold one transform, so the block size fixes N; 64-thread blocks serve every
+    // N <= 1024, of which 512 (C4) and 1024 (C2) get compile-time builds
     switch (l.block) {
-    case 64: if (l.stage) KB_FFT(64, true); else KB_FFT(64, false);
-    case 128: KB_FFT(128, true);
+    case 64:
+        if (g.log2NPhi == 10) KB_FFT(64, true, 10);
+        if (g.log2NPhi == 9) KB_FFT(64, true, 9);
+        if (l.stage) KB_FFT(64, true, 0); else KB_FFT(64, false, 0);
+    case 128: KB_FFT(128, true, 11);
     // (r02a A/B: capping the 256-thread kernels at 80 registers for three blocks per SM is a loss at
     // 2048 x 4096: forward 54.9 vs 47.5 us, inverse 64.3 vs 59.1 us)
-    case 256: KB_FFT(256, true);
-    case 512: KB_FFT(512, false);
-    case 1024: KB_FFT(1024, false);
+    case 256: KB_FFT(256, true, 12);
+    case 512: KB_FFT(512, false, 13);
+    case 1024: KB_FFT(1024, false, 14);
     default: return cudaErrorInvalidValue;
     }
 #undef KB_FFT
