@@ -82,23 +82,45 @@ class _Rank:
                 "halo_bytes_per_step": hb.value, "transpose_bytes_per_step": tb.value}
 
 
+def band_of(nTheta, world, rank):
+    """(first row, one past the last row) of a rank: the partition kamino_dist_create uses (csrc/dist.cu)."""
+    if world < 1 or world & (world - 1) or nTheta % world:
+        raise ValueError("world must be a power of two that divides nTheta")
+    rows = nTheta // world
+    if world > 1 and (rows < 32 or rows % 8):
+        raise ValueError("bands need at least 32 rows and a multiple of 8 wavenumbers per rank")
+    return rank * rows, (rank + 1) * rows
+
+
+def broadcast_unique_id(make_id, device=None):
+    """Rank 0 calls make_id() -> 128 bytes (kamino_dist_unique_id); every rank of the torch.distributed group returns them.
+    The one use of torch.distributed on the band-decomposed path."""
+    import torch
+    import torch.distributed as dist
+    payload = bytes(make_id()) if dist.get_rank() == 0 else bytes(128)
+    assert len(payload) == 128
+    dev = torch.device("cuda", device) if (dist.get_backend() == "nccl" and device is not None) else torch.device("cpu")
+    t = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
 class DistributedSolver(_Rank):
     """One rank under torch.distributed (any backend that can broadcast 128 bytes). Collective constructor."""
 
     def __init__(self, nTheta, radius, dt, device=0):
-        import torch
         import torch.distributed as dist
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
         lib = capi.load()
-        ident = (ctypes.c_ubyte * 128)()
+        ident = None
         if world > 1:
-            if rank == 0:
-                _check(lib.kamino_dist_unique_id(ident))
-            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
-            t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
-            dist.broadcast(t, src=0)
-            ident = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
-        super().__init__(nTheta, radius, dt, rank, world, device, ident if world > 1 else None)
+            def make_id():
+                buf = (ctypes.c_ubyte * 128)()
+                _check(lib.kamino_dist_unique_id(buf))
+                return bytes(buf)
+            ident = (ctypes.c_ubyte * 128)(*broadcast_unique_id(make_id, device))
+        super().__init__(nTheta, radius, dt, rank, world, device, ident)
+        assert (self.lo, self.hi) == band_of(nTheta, world, rank)
 
     def step(self, nSteps=1):
         _check(self.lib.kamino_dist_step(self.handle, nSteps), self.handle)
