@@ -245,6 +245,21 @@ int kamino_init_velocity_host_rows(int nTheta, float radius, int rowBegin, int r
 long kamino_particle_count(int nTheta, float particleDensity);
 int kamino_seed_particles_host(int nTheta, float particleDensity, float* coords);
 
+/* ---- GPU-side initialisers (no reference counterpart: its initialisers are serial host loops) ---- */
+
+/* The FBM initial velocity of kernel/KaminoInitializer.cu:3-134 evaluated on the device, operation for operation,
+ * into the "this step" velocity buffers of every simulation of the context (of the rank's band for a kamino_dist).
+ * Differs from kamino_init_velocity_host only where CUDA's double sin() and glibc's straddle an fp32 rounding boundary
+ * inside the lattice hash (about 1e-8 of the evaluations; measured in tests/test_parity_gpu.py). For start-up at sizes
+ * where the host loop costs minutes; the drop-in classes keep the bit-identical host initialiser. */
+int kamino_init_velocity_device(kamino_ctx* ctx);
+int kamino_dist_init_velocity_device(kamino_dist* d);
+/* The particle lattice of kernel/KaminoParticles.cu:20-62 (same counts, spacing, jitter range, clamp and index order)
+ * with the four uniforms of every particle taken from a counter-based generator (splitmix64 of (seed, index)) instead
+ * of libc rand(): reproducible for a seed on any device, NOT the reference's sequence. The context must hold
+ * kamino_particle_count(nTheta, particleDensity) particles (kamino_alloc_particles), else KAMINO_ERR_STATE. */
+int kamino_seed_particles_device(kamino_ctx* ctx, float particleDensity, unsigned long long seed);
+
 /* ---- parity instrumentation ------------------------------------------------------------ */
 
 /* Evaluate, on the device, the index / predicate part of the reference's samplers

@@ -80,6 +80,9 @@ SIGNATURES = {
     "kamino_dist_comm_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),
                                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "kamino_init_velocity_device": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_dist_init_velocity_device": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_seed_particles_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_ulonglong]),
     "kamino_particle_count": (ctypes.c_long, [ctypes.c_int, ctypes.c_float]),
     "kamino_seed_particles_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_void_p]),
     "kamino_debug_locate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,

@@ -506,6 +506,17 @@ int kamino_dist_download(kamino_dist* d, int field, float* hostRows)
     return 0;
 }
 
+// the reference's FBM initial velocity for this rank's rows, evaluated on the device (device_init.cu)
+int kamino_dist_init_velocity_device(kamino_dist* d)
+{
+    if (!d) return fail(nullptr, KAMINO_ERR_INVALID, "null band context");
+    DeviceGuard guard(d->device);
+    cudaError_t e = launchInitVelocity(d->g, d->velPhi[d->velIdx], d->velTheta[d->velIdx], d->lo, d->rows, d->stream);
+    if (e != cudaSuccess) return fail(d, (int)e, "kamino_dist_init_velocity_device");
+    KD_TRY(d, cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
 int kamino_dist_step(kamino_dist* d, int nSteps)
 {
     if (!d) return fail(nullptr, KAMINO_ERR_INVALID, "null band context");

@@ -562,6 +562,36 @@ int kamino_project(kamino_ctx* ctx)
     return timedPhase(ctx, ctx->projectionTime, [&](IndexState& st) { return enqueueProject(ctx, st, ctx->stream); });
 }
 
+// GPU-side initialisers (device_init.cu): every simulation of the batch gets the same field / lattice
+int kamino_init_velocity_device(kamino_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    for (int sim = 0; sim < ctx->batch; ++sim) {
+        cudaError_t e = launchInitVelocity(ctx->g, ctx->velPhi[ctx->velIdx] + (size_t)sim * ctx->g.cells,
+                                           ctx->velTheta[ctx->velIdx] + (size_t)sim * ctx->g.cells, 0, ctx->g.nTheta, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, (int)e, "kamino_init_velocity_device");
+    }
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int kamino_seed_particles_device(kamino_ctx* ctx, float particleDensity, unsigned long long seed)
+{
+    if (!ctx) return fail(nullptr, KAMINO_ERR_INVALID, "null context");
+    if (!(particleDensity >= 0.f)) return fail(ctx, KAMINO_ERR_INVALID, "particleDensity < 0");
+    DeviceGuard guard(ctx->device);
+    for (int sim = 0; sim < ctx->batch; ++sim) {
+        cudaError_t e = launchSeedParticles(ctx->g.nTheta, particleDensity, seed,
+                                            ctx->particles[ctx->particleIdx] + (size_t)sim * 2 * ctx->g.numParticles, ctx->g.numParticles, ctx->stream);
+        if (e != cudaSuccess)
+            return fail(ctx, e == cudaErrorInvalidValue ? KAMINO_ERR_STATE : (int)e,
+                        "kamino_seed_particles_device (allocate kamino_particle_count(nTheta, particleDensity) particles first)");
+    }
+    KB_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // Parity instrumentation: kamino_project with the theta solve done in the reference's cyclic-reduction order
 // (debug_cr.cu). Never part of a step graph.
 int kamino_debug_project_cr(kamino_ctx* ctx)

@@ -114,6 +114,11 @@ cudaError_t launchInverseFFTGradient(const GridParams& g, const SpectralTables& 
 // parity instrumentation (debug_cr.cu): the theta solve in the reference's cyclic-reduction order, in place
 cudaError_t launchCyclicReductionDebug(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, cudaStream_t stream);
 
+// GPU-side initialisers (device_init.cu): the FBM initial velocity of rows [rowBegin, rowBegin + rowCount) into buffers
+// addressed with global row indices, and the counter-based particle lattice (expected = the allocated particle count)
+cudaError_t launchInitVelocity(const GridParams& g, float* velPhi, float* velTheta, int rowBegin, int rowCount, cudaStream_t stream);
+cudaError_t launchSeedParticles(int nTheta, float particleDensity, unsigned long long seed, float* coords, long expected, cudaStream_t stream);
+
 // host: the constants block of the samplers for this grid
 // (validLo, validHi, haloViolation: the resident row range and the device flag of a theta-band context, dist.cu)
 void fillSamplerConsts(const GridParams& g, void* hostBlock64, int validLo = 0, int validHi = -1, int* haloViolation = nullptr);

@@ -70,6 +70,9 @@ class _Rank:
         self.upload(capi.VEL_THETA, v[:self.rows_of(capi.VEL_THETA)])
         return u, v
 
+    def init_velocity_on_device(self):
+        _check(self.lib.kamino_dist_init_velocity_device(self.handle), self.handle)
+
     def sync(self):
         _check(self.lib.kamino_dist_sync(self.handle), self.handle)
 

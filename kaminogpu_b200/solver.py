@@ -173,6 +173,18 @@ class KaminoSolver:
             for q in (self.velPhi, self.velTheta):
                 capi.check(self._lib.kamino_upload_field(self._ctx, q._field, sim, _ptr(q.cpuBuffer)), self._ctx)
 
+    def initialize_velocity_on_device(self):
+        """The same FBM field evaluated by a CUDA kernel (kamino_init_velocity_device): start-up of large grids."""
+        capi.check(self._lib.kamino_init_velocity_device(self._ctx), self._ctx)
+
+    def seed_particles_on_device(self, particleDensity, seed):
+        """The reference's particle lattice with counter-based jitter (kamino_seed_particles_device)."""
+        n = int(self._lib.kamino_particle_count(self.nTheta, ctypes.c_float(particleDensity)))
+        self.particles = KaminoParticles(self, 0.0, self.gridLen, self.nTheta, coords=np.zeros(2 * n, np.float32))
+        capi.check(self._lib.kamino_alloc_particles(self._ctx, n), self._ctx)
+        capi.check(self._lib.kamino_seed_particles_device(self._ctx, ctypes.c_float(particleDensity),
+                                                          ctypes.c_ulonglong(seed)), self._ctx)
+
     def initDensityfromPic(self, path):
         """kernel/KaminoSolver.cu:243-277: a no-op for "" (image input is out of scope)."""
         if path:

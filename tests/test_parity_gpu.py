@@ -738,6 +738,61 @@ def test_dist_reports_a_backtrace_that_leaves_the_halo(K):
         grp.close()
 
 
+# ---- GPU-side initialisers ----------------------------------------------------------------
+
+@pytest.mark.parametrize("nT", [128, 512])
+def test_device_velocity_initialiser_against_the_host_one(K, nT):
+    """kamino_init_velocity_device restates the reference's FBM initialiser as device code, operation for operation;
+    only CUDA's double sin() inside the lattice hash can differ from glibc's (where the two results straddle an fp32
+    rounding boundary). Measured identical fraction is printed; bars: >= 99.99 % identical words, relative L2 <= 1e-6."""
+    u, v = oa.init_velocity(nT)
+    with K.KaminoSolver(2 * nT, nT, 5.0, 0.005, initVelocity=False) as s:
+        s.initialize_velocity_on_device()
+        st = state(s)
+    for name, want in (("velPhi", u), ("velTheta", v)):
+        w, e = words_equal(st[name], want), oa.rel_l2(st[name], want)
+        print("device initialiser nTheta %d %-8s identical words %.6f relL2 %.2e" % (nT, name, w, e))
+        assert w >= 0.9999 and e <= 1e-6
+
+
+def test_device_velocity_initialiser_of_a_band_equals_the_whole_grid(K):
+    from kaminogpu_b200 import capi, dist
+    nT, world = 128, 4
+    with K.KaminoSolver(2 * nT, nT, 5.0, 0.005, initVelocity=False) as s:
+        s.initialize_velocity_on_device()
+        st = state(s)
+    grp = dist.LocalGroup(nT, 5.0, 0.005, world)
+    try:
+        for r in grp.ranks:
+            r.init_velocity_on_device()
+        assert np.array_equal(grp.gather(capi.VEL_PHI).ravel(), st["velPhi"])
+        assert np.array_equal(grp.gather(capi.VEL_THETA).ravel(), st["velTheta"])
+    finally:
+        grp.close()
+
+
+def test_device_particle_seeding_is_the_reference_lattice_with_counter_based_jitter(K):
+    nT, dens = 64, 4.0
+    spacing = np.float32(np.pi / nT / 2.0)
+    def seeded(seed):
+        with K.KaminoSolver(2 * nT, nT, 5.0, 0.005, initVelocity=False) as s:
+            s.seed_particles_on_device(dens, seed)
+            return s.particles.copyBack2CPU().reshape(-1, 2).copy()
+    a, b, c = seeded(1234), seeded(1234), seeded(99)
+    numTheta = int(np.float32(2.0) * nT)
+    assert a.shape == (2 * numTheta * numTheta, 2)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)            # reproducible per seed
+    i, j = np.divmod(np.arange(a.shape[0]), numTheta)                   # index i * numTheta + j (KaminoParticles.cu:59)
+    assert np.all(np.abs(a[:, 0] - i * spacing) <= spacing / 2 * 1.0001) and np.all(np.abs(a[:, 1] - j * spacing) <= spacing / 2 * 1.0001)
+    assert a.min() >= 0.0                                               # clamped at 0 (:49-54)
+    jitter = (a[:, 0] - i * spacing)[i > 0] / (spacing / 2)
+    assert abs(jitter.mean()) < 0.02 and 0.55 < jitter.std() < 0.60     # uniform on [-1, 1]: std 1 / sqrt(3)
+    with K.KaminoSolver(2 * nT, nT, 5.0, 0.005, initVelocity=False) as s:      # wrong particle count is refused
+        from kaminogpu_b200 import capi
+        capi.check(s._lib.kamino_alloc_particles(s._ctx, 10), s._ctx)
+        assert s._lib.kamino_seed_particles_device(s._ctx, ctypes.c_float(dens), ctypes.c_ulonglong(1)) == capi_err("STATE")
+
+
 # ---- theta-band decomposition, Python prototype + SPIKE research path (banded.py): virtual ranks on one GPU ----
 
 @pytest.mark.parametrize("nT,world", [(128, 4), (256, 2)])
