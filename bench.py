@@ -539,6 +539,7 @@ def main():
         d.upload(capi.DENSITY, 0.5 + 0.5 * np.sin(4 * ph_v) * np.sin(th_u) ** 2)
         t_init = time.perf_counter() - t_init
         ext = torch.cuda.ExternalStream(d.cuda_stream)
+        peer5, note5 = d.transport()
         d.step(3)
         d.sync()
         breps = []
@@ -567,11 +568,16 @@ def main():
                   "steps": steps5, "reps": len(breps), "finite": fin5, "dt": C5["dt"], "radius": C5["radius"],
                   "initial_field": "analytic (two low wavenumber modes per component, max |u| 0.15)",
                   "device_gb_per_rank": mem / 1e9, "init_s": t_init,
-                  "collectives": "none (one band)" if world == 1 else "NCCL send/recv: 24-row halos + two transposes of the half spectrum per step",
+                  "collectives": "none (one band)" if world == 1 else
+                                 ("NCCL send/recv of 24-row halos; the two transposes of the half spectrum are peer-memory stores of the FFT and "
+                                  "theta-solve kernels over NVLink (%s) + one NCCL barrier each" % note5 if peer5 else
+                                  "NCCL send/recv: 24-row halos + two transposes of the half spectrum per step (%s)" % note5),
+                  "peer_memory_transposes": peer5,
                   "transpose_bytes_sent_per_rank_per_step": cs["transpose_bytes_per_step"],
                   "halo_bytes_sent_per_rank_per_step": cs["halo_bytes_per_step"],
                   "transpose_ms_per_step": tsec[0] * 1e3, "halo_ms_per_step": tsec[1] * 1e3,
-                  "transpose_gbs_per_rank": (cs["transpose_bytes_per_step"] / tsec[0] / 1e9) if world > 1 and tsec[0] > 0 else None}
+                  "transpose_note": "time between the kernels around each transpose: the barrier when the kernels store into peer memory, the NCCL send/recv otherwise",
+                  "transpose_gbs_per_rank": (cs["transpose_bytes_per_step"] / tsec[0] / 1e9) if world > 1 and tsec[0] > 0 and not peer5 else None}
 
     if rank == 0:
         sims = batch * world

@@ -225,6 +225,12 @@ int kamino_dist_group_step(kamino_dist* const* ranks, int world, int nSteps);
  * since the last call (theta-CFL too large for the decomposition: the run no longer equals the single-GPU one). */
 int kamino_dist_sync(kamino_dist* d);
 int kamino_dist_stream(kamino_dist* d, void** cudaStream);
+/* Transport of the two transposes around the theta solve. usesPeerStores = 1: the FFT kernel and the theta solve store
+ * straight into the owning ranks' buffers over NVLink (CUDA IPC mappings of the peers' memory, set up at creation; the
+ * default whenever every rank could map every peer), the transposes reduce to a barrier each; 0: NCCL send / recv of
+ * staged buffers. setPeerStores = 1 / 0 switches (collective: every rank must make the same call; -1 only queries);
+ * note receives a short text saying how the peers are mapped or why they are not. Results are bit-identical either way. */
+int kamino_dist_transport(kamino_dist* d, int setPeerStores, int* usesPeerStores, const char** note);
 /* Communication accounting. enable = 1 / 0 switches per-step CUDA-event brackets around the NCCL calls on / off
  * (it adds one host synchronisation per step; -1 leaves the setting); the accumulated seconds and bytes SENT per
  * step by this rank are returned. */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "kamino_dist_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kamino_dist_group_step": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]),
     "kamino_dist_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "kamino_dist_transport": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_char_p)]),
     "kamino_dist_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "kamino_dist_comm_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long),

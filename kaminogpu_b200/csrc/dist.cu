@@ -28,9 +28,15 @@
 //   4. theta solve of my K slots over all rows, in place on `packed`
 //   5. transpose back: packed[rows of p, + 1] -> rank p's specBack[me]               (P sends + P receives)
 //   6. inverse FFT + gradient on [lo, hi) reading specBack
-// Everything of a rank is ordered on one stream. Transport: NCCL (one process per GPU, the unique id is
-// distributed by the caller), or -- for P virtual ranks inside one process on one device, which is what the
-// single-GPU parity tests drive -- plain device copies (kamino_dist_group_step).
+// Everything of a rank is ordered on one stream. Transport of the two transposes (3, 5):
+//   * peer memory (default when the peers' memory can be mapped): the FFT kernel of step 2 stores every block of its
+//     spectrum straight into the owner's `packed`, and the theta solve of step 4 stores its solution straight into the
+//     owners' `specBack`, over NVLink -- compute and transfer are ONE kernel each, tile by tile; what is left of 3 and 5
+//     is a barrier (a one-word NCCL all-reduce). Peer pointers: CUDA IPC mappings of the other ranks' arenas, exchanged
+//     through NCCL itself at creation.
+//   * NCCL send / recv of the staged buffers (fallback; kamino_dist_transport switches).
+// The halos go through NCCL send / recv either way. For P virtual ranks inside one process on one device -- what the
+// single-GPU parity tests drive -- kamino_dist_group_step uses sibling pointers / plain device copies instead.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -49,6 +55,7 @@ namespace {
 constexpr int kHalo = 24;          // rows exchanged with each neighbour
 constexpr int kAdvectExtra = 16;   // rows beyond the band that the advection recomputes
 constexpr int kGeoExtra = 8;       // rows beyond the band that the geometric phase recomputes
+constexpr int kMaxPeers = 16;      // ranks whose buffers a rank can address (peer-memory transposes)
 
 // NCCL is loaded at run time: single-GPU users of the library need no NCCL installed, and inside a process
 // that already carries one (torch) the same instance is shared.
@@ -59,6 +66,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -84,6 +93,8 @@ const NcclApi* ncclApi()
         a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
         a.Send = (decltype(a.Send))sym("ncclSend");
         a.Recv = (decltype(a.Recv))sym("ncclRecv");
+        a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+        a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
         a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
         a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
         a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
@@ -120,6 +131,17 @@ struct kamino_dist {
     int* haloViolation = nullptr;          // device flag
     int velIdx = 0, densityIdx = 0;
     ncclComm_t comm = nullptr;
+    // Peer-memory transposes: the FFT kernel stores every block of its spectrum straight into the owner's `packed`
+    // buffer and the theta solve stores its solution straight into the owners' `specBack` buffers, over NVLink (peer
+    // pointers: CUDA IPC mappings of the other ranks' arenas, or sibling ranks of the same process); what is left of the
+    // two transposes is a barrier each. Tables of world pointers in device memory, read by the kernels.
+    bool peerStores = false;               // transposes through peer memory (else NCCL send / recv, or copies)
+    bool peersLinked = false;
+    float2** peerPackedTable = nullptr;    // device: [world]
+    float2** peerBackTable = nullptr;      // device: [world]
+    void* ipcBase[kMaxPeers]{};            // mappings to close at destruction
+    int* barrierWord = nullptr;            // device: operand of the barrier all-reduce
+    std::string peerNote = "not attempted";
     cudaEvent_t ev[6]{};                   // comm timing brackets
     bool timing = false;
     double haloSeconds = 0.0, transposeSeconds = 0.0;
@@ -184,7 +206,9 @@ GridParams rowsOf(const kamino_dist* d, int begin, int end)
     return g;
 }
 
-// phases 2a-2c of the header: advection, geometric, divergence + FFT into the send layout
+SpectrumLayout forwardLayout(const kamino_dist* d);
+
+// phases 2a-2c of the header: advection, geometric, divergence + FFT into the send layout (or straight into the peers)
 cudaError_t enqueueToSpectrum(kamino_dist* d)
 {
     AdvectArgs a{};
@@ -200,19 +224,22 @@ cudaError_t enqueueToSpectrum(kamino_dist* d)
                         d->velPhi[d->velIdx ^ 1], d->velTheta[d->velIdx ^ 1], 1, d->stream);
     if (e != cudaSuccess) return e;
     d->velIdx ^= 1;
-    const SpectrumLayout lay{d->lo, d->kper, d->log2Kper, (size_t)d->rows * d->kper};
+    const SpectrumLayout lay = forwardLayout(d);
     return launchDivergenceFFT(rowsOf(d, d->lo, d->hi), d->tables, d->velPhi[d->velIdx], d->velTheta[d->velIdx], d->specSend, 1, d->stream, &lay);
 }
 
 cudaError_t enqueueSolve(kamino_dist* d)
 {
     // my wavenumber band over ALL rows; the tables hold this band only (slot index from 0)
-    return launchTridiagonalBand(d->g, d->tables, d->packed, d->kper, 0, d->kper, 1, d->stream);
+    int log2Rows = 0;
+    while ((1 << log2Rows) < d->rows) ++log2Rows;
+    const PeerScatter scatter{d->peerBackTable, log2Rows, d->rank, d->kper};
+    return launchTridiagonalBand(d->g, d->tables, d->packed, d->kper, 0, d->kper, 1, d->stream, d->peerStores ? &scatter : nullptr);
 }
 
 cudaError_t enqueueInverse(kamino_dist* d)
 {
-    const SpectrumLayout lay{d->lo, d->kper, d->log2Kper, (size_t)(d->rows + 1) * d->kper};
+    const SpectrumLayout lay{d->lo, d->kper, d->log2Kper, (size_t)(d->rows + 1) * d->kper, nullptr};
     return launchInverseFFTGradient(rowsOf(d, d->lo, d->hi), d->tables, d->specBack, d->velPhi[d->velIdx], d->velTheta[d->velIdx],
                                     d->pressure, 1, d->stream, &lay);
 }
@@ -268,6 +295,82 @@ int transposeBackwardNccl(kamino_dist* d)
     return 0;
 }
 
+// all ranks have reached this point of their streams (and their earlier writes into peer memory are complete: a kernel's
+// stores are visible device-wide -- and system-wide for peer mappings -- once the kernel has finished, and the all-reduce
+// kernel is ordered after it on the stream)
+int barrierNccl(kamino_dist* d)
+{
+    const NcclApi* n = ncclApi();
+    KD_NCCL(d, n->AllReduce(d->barrierWord, d->barrierWord, 1, ncclInt, ncclSum, d->comm, d->stream));
+    return 0;
+}
+
+// upload the two pointer tables (host arrays of `world` device pointers)
+int uploadPeerTables(kamino_dist* d, float2* const* packedOf, float2* const* backOf)
+{
+    KD_TRY(d, cudaMemcpyAsync(d->peerPackedTable, packedOf, sizeof(float2*) * d->world, cudaMemcpyHostToDevice, d->stream));
+    KD_TRY(d, cudaMemcpyAsync(d->peerBackTable, backOf, sizeof(float2*) * d->world, cudaMemcpyHostToDevice, d->stream));
+    KD_TRY(d, cudaStreamSynchronize(d->stream));
+    d->peersLinked = true;
+    return 0;
+}
+
+// NCCL ranks: exchange CUDA IPC handles of the arenas (through NCCL itself: no other channel is needed), map the peers,
+// agree on the outcome. Any failure anywhere leaves every rank on the NCCL transposes.
+struct PeerRecord { cudaIpcMemHandle_t handle; unsigned long long offPacked, offBack; };
+
+int linkPeersOverIpc(kamino_dist* d)
+{
+    const NcclApi* n = ncclApi();
+    if (d->world > kMaxPeers) { d->peerNote = "more ranks than peer slots"; return 0; }
+    PeerRecord mine{};
+    bool ok = cudaIpcGetMemHandle(&mine.handle, d->arena) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    mine.offPacked = (unsigned long long)((char*)d->packed - d->arena);
+    mine.offBack = (unsigned long long)((char*)d->specBack - d->arena);
+    PeerRecord* dev = nullptr;
+    KD_TRY(d, cudaMalloc((void**)&dev, sizeof(PeerRecord) * d->world));
+    KD_TRY(d, cudaMemcpyAsync(dev + d->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, d->stream));
+    ncclResult_t r = n->AllGather(dev + d->rank, dev, sizeof(PeerRecord), ncclChar, d->comm, d->stream);
+    std::vector<PeerRecord> all(d->world);
+    if (r == ncclSuccess) {
+        cudaMemcpyAsync(all.data(), dev, sizeof(PeerRecord) * d->world, cudaMemcpyDeviceToHost, d->stream);
+        ok = ok && cudaStreamSynchronize(d->stream) == cudaSuccess;
+    } else ok = false;
+    cudaFree(dev);
+    float2* packedOf[kMaxPeers]{};
+    float2* backOf[kMaxPeers]{};
+    for (int p = 0; p < d->world && ok; ++p) {
+        if (p == d->rank) { packedOf[p] = d->packed; backOf[p] = d->specBack; continue; }
+        void* base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        d->ipcBase[p] = base;
+        packedOf[p] = (float2*)((char*)base + all[p].offPacked);
+        backOf[p] = (float2*)((char*)base + all[p].offBack);
+    }
+    // unanimous?
+    int flag = ok ? 1 : 0;
+    KD_TRY(d, cudaMemcpyAsync(d->barrierWord, &flag, sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    KD_NCCL(d, n->AllReduce(d->barrierWord, d->barrierWord, 1, ncclInt, ncclMin, d->comm, d->stream));
+    KD_TRY(d, cudaMemcpyAsync(&flag, d->barrierWord, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    KD_TRY(d, cudaStreamSynchronize(d->stream));
+    KD_TRY(d, cudaMemsetAsync(d->barrierWord, 0, sizeof(int), d->stream));
+    if (!flag) {
+        d->peerNote = ok ? "a peer could not map this rank's memory (CUDA IPC)" : "CUDA IPC mapping of a peer's memory failed";
+        return 0;
+    }
+    if (int rc = uploadPeerTables(d, packedOf, backOf)) return rc;
+    d->peerStores = true;
+    d->peerNote = "CUDA IPC mappings of the peers' arenas";
+    return 0;
+}
+
+SpectrumLayout forwardLayout(const kamino_dist* d)
+{
+    if (d->peerStores) return SpectrumLayout{0, d->kper, d->log2Kper, 0, d->peerPackedTable};
+    return SpectrumLayout{d->lo, d->kper, d->log2Kper, (size_t)d->rows * d->kper, nullptr};
+}
+
 int stepNccl(kamino_dist* d)
 {
     const bool t = d->timing;
@@ -277,12 +380,12 @@ int stepNccl(kamino_dist* d)
     cudaError_t e = enqueueToSpectrum(d);
     if (e != cudaSuccess) return fail(d, (int)e, "advection / geometric / divergence + FFT launch");
     if (t) KD_TRY(d, cudaEventRecord(d->ev[2], d->stream));
-    if (int rc = transposeForwardNccl(d)) return rc;
+    if (int rc = d->peerStores ? barrierNccl(d) : transposeForwardNccl(d)) return rc;
     if (t) KD_TRY(d, cudaEventRecord(d->ev[3], d->stream));
     e = enqueueSolve(d);
     if (e != cudaSuccess) return fail(d, (int)e, "theta solve launch");
     if (t) KD_TRY(d, cudaEventRecord(d->ev[4], d->stream));
-    if (int rc = transposeBackwardNccl(d)) return rc;
+    if (int rc = d->peerStores ? barrierNccl(d) : transposeBackwardNccl(d)) return rc;
     if (t) KD_TRY(d, cudaEventRecord(d->ev[5], d->stream));
     e = enqueueInverse(d);
     if (e != cudaSuccess) return fail(d, (int)e, "inverse FFT + gradient launch");
@@ -380,7 +483,7 @@ int kamino_dist_create(kamino_dist** out, int device, int nTheta, float radius, 
     const size_t slotRows = (size_t)nTheta * kper;
     const size_t tableBytes = alignUp(sizeof(float2) * N, 256) + 10 * alignUp(sizeof(float) * nTheta, 256) + 256
                             + 5 * alignUp(sizeof(float) * slotRows, 256) + alignUp(sizeof(float) * (size_t)(nTheta / 4) * kper, 256) + 256;
-    d->arenaBytes = 7 * fieldBytes + sendBytes + packedBytes + backBytes + tableBytes;
+    d->arenaBytes = 7 * fieldBytes + sendBytes + packedBytes + backBytes + tableBytes + 1024;
     cudaError_t e = cudaMalloc((void**)&d->arena, d->arenaBytes);
     if (e != cudaSuccess) { int rc = fail(nullptr, (int)e, "cudaMalloc(band arena)"); delete d; return rc; }
     // cudaMemset on the legacy stream is asynchronous for device memory and does NOT order against the non-blocking
@@ -420,6 +523,9 @@ int kamino_dist_create(kamino_dist** out, int device, int nTheta, float radius, 
     t.thDelta = (float*)take(sizeof(float) * slotRows);
     t.thBetaEnd = (float*)take(sizeof(float) * (size_t)(nTheta / 4) * kper);
     t.minusTwoOverH2 = -2.0 / (double)(g.h * g.h);
+    d->peerPackedTable = (float2**)take(sizeof(float2*) * kMaxPeers);
+    d->peerBackTable = (float2**)take(sizeof(float2*) * kMaxPeers);
+    d->barrierWord = (int*)take(256);
 
     int prioLeast = 0, prioGreatest = 0;
     cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
@@ -446,6 +552,7 @@ int kamino_dist_create(kamino_dist** out, int device, int nTheta, float radius, 
         memcpy(&id, id128, sizeof(id));
         ncclResult_t r = ncclApi()->CommInitRank(&d->comm, world, id, rank);
         if (r != ncclSuccess) { int rc = failNccl(nullptr, r, "ncclCommInitRank"); kamino_dist_destroy(d); return rc; }
+        if (int rc = linkPeersOverIpc(d)) { g_distCreateError = d->lastError; kamino_dist_destroy(d); return rc; }
     }
     *out = d;
     return 0;
@@ -456,6 +563,7 @@ int kamino_dist_destroy(kamino_dist* d)
     if (!d) return 0;
     DeviceGuard guard(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
+    for (void* base : d->ipcBase) if (base) cudaIpcCloseMemHandle(base);
     if (d->comm && ncclApi()) ncclApi()->CommDestroy(d->comm);
     for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -551,6 +659,18 @@ int kamino_dist_group_step(kamino_dist* const* ranks, int world, int nSteps)
     kamino_dist* d0 = ranks[0];
     DeviceGuard guard(d0->device);
     const size_t N = (size_t)d0->g.nPhi;
+    // peer-memory transposes between the virtual ranks: their buffers are plain pointers of this process
+    const bool peerStores = d0->peerStores;
+    for (int r = 0; r < world; ++r)
+        if (ranks[r]->peerStores != peerStores) return fail(d0, KAMINO_ERR_STATE, "group members disagree on the transpose transport");
+    if (peerStores && world <= kMaxPeers) {
+        float2* packedOf[kMaxPeers]{};
+        float2* backOf[kMaxPeers]{};
+        for (int r = 0; r < world; ++r) { packedOf[r] = ranks[r]->packed; backOf[r] = ranks[r]->specBack; }
+        for (int r = 0; r < world; ++r)
+            if (!ranks[r]->peersLinked)
+                if (int rc = uploadPeerTables(ranks[r], packedOf, backOf)) return rc;
+    }
     auto barrier = [&]() -> cudaError_t {
         for (int r = 0; r < world; ++r) {
             cudaError_t e = cudaStreamSynchronize(ranks[r]->stream);
@@ -576,21 +696,25 @@ int kamino_dist_group_step(kamino_dist* const* ranks, int world, int nSteps)
         }
         KD_TRY(d0, barrier());
         const size_t block = (size_t)d0->rows * d0->kper;
-        for (int r = 0; r < world; ++r)
-            for (int p = 0; p < world; ++p)                 // r's block for p -> p's packed rows of r
-                KD_TRY(d0, cudaMemcpyAsync(ranks[p]->packed + r * block, ranks[r]->specSend + p * block, sizeof(float2) * block,
-                                           cudaMemcpyDeviceToDevice, ranks[p]->stream));
-        KD_TRY(d0, barrier());
+        if (!peerStores) {
+            for (int r = 0; r < world; ++r)
+                for (int p = 0; p < world; ++p)             // r's block for p -> p's packed rows of r
+                    KD_TRY(d0, cudaMemcpyAsync(ranks[p]->packed + r * block, ranks[r]->specSend + p * block, sizeof(float2) * block,
+                                               cudaMemcpyDeviceToDevice, ranks[p]->stream));
+            KD_TRY(d0, barrier());
+        }
         for (int r = 0; r < world; ++r) {
             cudaError_t e = enqueueSolve(ranks[r]);
             if (e != cudaSuccess) return fail(d0, (int)e, "theta solve launch");
         }
         KD_TRY(d0, barrier());
-        for (int r = 0; r < world; ++r)
-            for (int p = 0; p < world; ++p)                 // r's solution rows of p (+1) -> p's specBack block r
-                KD_TRY(d0, cudaMemcpyAsync(ranks[p]->specBack + (size_t)r * (d0->rows + 1) * d0->kper, ranks[r]->packed + (size_t)p * block,
-                                           sizeof(float2) * (size_t)backRows(d0, p) * d0->kper, cudaMemcpyDeviceToDevice, ranks[p]->stream));
-        KD_TRY(d0, barrier());
+        if (!peerStores) {
+            for (int r = 0; r < world; ++r)
+                for (int p = 0; p < world; ++p)             // r's solution rows of p (+1) -> p's specBack block r
+                    KD_TRY(d0, cudaMemcpyAsync(ranks[p]->specBack + (size_t)r * (d0->rows + 1) * d0->kper, ranks[r]->packed + (size_t)p * block,
+                                               sizeof(float2) * (size_t)backRows(d0, p) * d0->kper, cudaMemcpyDeviceToDevice, ranks[p]->stream));
+            KD_TRY(d0, barrier());
+        }
         for (int r = 0; r < world; ++r) {
             cudaError_t e = enqueueInverse(ranks[r]);
             if (e != cudaSuccess) return fail(d0, (int)e, "inverse FFT + gradient launch");
@@ -606,6 +730,22 @@ int kamino_dist_sync(kamino_dist* d)
     DeviceGuard guard(d->device);
     KD_TRY(d, cudaStreamSynchronize(d->stream));
     return d->world > 1 ? checkViolation(d) : 0;
+}
+
+int kamino_dist_transport(kamino_dist* d, int setPeerStores, int* usesPeerStores, const char** note)
+{
+    if (!d) return fail(nullptr, KAMINO_ERR_INVALID, "null band context");
+    if (setPeerStores >= 0) {
+        const bool want = setPeerStores != 0;
+        if (want && d->comm && !d->peersLinked) return fail(d, KAMINO_ERR_STATE, "peer memory is not mapped: " + d->peerNote);
+        if (want && d->world > kMaxPeers) return fail(d, KAMINO_ERR_STATE, "more ranks than peer slots");
+        DeviceGuard guard(d->device);
+        KD_TRY(d, cudaStreamSynchronize(d->stream));
+        d->peerStores = want && d->world > 1;
+    }
+    if (usesPeerStores) *usesPeerStores = d->peerStores ? 1 : 0;
+    if (note) *note = d->peerNote.c_str();
+    return 0;
 }
 
 int kamino_dist_stream(kamino_dist* d, void** cudaStream)

@@ -89,7 +89,14 @@ cudaError_t launchBuildTables(const GridParams& g, SpectralTables t, cudaStream_
 // source rank), element (row, k) sits at (k >> log2Block) * blockPitch + (row - rowBase) * rowPitch +
 // (k & (2^log2Block - 1)). The forward FFT stores straight into the send buffer of the all-to-all and the
 // inverse FFT reads straight from its receive buffer: no pack / unpack passes.
-struct SpectrumLayout { int rowBase, rowPitch, log2Block; size_t blockPitch; };
+// peerTable != NULL (peer-memory transposes): block b of slots is not stored locally but straight into rank b's buffer
+// peerTable[b] (a device pointer valid on this GPU: the rank's own memory, or a peer's mapped through CUDA IPC / the same
+// process), at [global row][slot within the block] with row pitch rowPitch -- the receive layout of the transpose.
+struct SpectrumLayout { int rowBase, rowPitch, log2Block; size_t blockPitch; float2* const* peerTable; };
+// Where the theta solve of a band-decomposed run puts its solution when the transposes go through peer memory: row i of
+// my K slots belongs to rank i >> log2Rows, whose buffer table[rank] holds [source rank][rows + 1][K]; the first row of a
+// band is also the extra row of the band above it. table == NULL: in place (single GPU, or NCCL transposes).
+struct PeerScatter { float2* const* table; int log2Rows, myRank, kper; };
 cudaError_t launchDivergenceFFT(const GridParams& g, const SpectralTables& t, const float* velPhi,
                                 const float* velTheta, float2* spectrum, int batch, cudaStream_t stream,
                                 const SpectrumLayout* packed = nullptr);
@@ -98,7 +105,8 @@ cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, floa
 // band-decomposed runs: solve slots [slotBegin, slotBegin + slotCount) whose right-hand sides sit in
 // `packed` as [theta][slot - slotBegin] with row pitch `pitch` (float2 elements), one simulation
 cudaError_t launchTridiagonalBand(const GridParams& g, const SpectralTables& t, float2* packed, int pitch,
-                                  int slotBegin, int slotCount, int tableBatch, cudaStream_t stream);
+                                  int slotBegin, int slotCount, int tableBatch, cudaStream_t stream,
+                                  const PeerScatter* scatter = nullptr);
 // band-local theta solve of the reduced-interface (SPIKE) mode: `band` holds th* tables built for rows
 // [rowBegin, rowBegin + rows) cut loose from their neighbours; only its th* members are used
 size_t bandSolveTableFloats(const GridParams& g, int rows);

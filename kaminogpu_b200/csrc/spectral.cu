@@ -232,16 +232,23 @@ divergenceFFTKernel(GridParams g, SpectralTables t, const float* __restrict__ ve
     if (!valid) return;
     const float scale = 0.5f / (float)N;
     // dense: [row][slot]; PACKED (theta bands, dist.cu): the send layout of the transpose, see SpectrumLayout
+    const bool peers = PACKED && lay.peerTable != nullptr;
     float2* rowA = PACKED ? spectrum + (size_t)(j - lay.rowBase) * lay.rowPitch : spectrum + (size_t)j * half;
     float2* rowB = rowA + (PACKED ? lay.rowPitch : half);
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         const int k = tt + (m << log2T);          // 0 .. N/2-1
-        const size_t at = PACKED ? (size_t)(k >> lay.log2Block) * lay.blockPitch + (k & ((1 << lay.log2Block) - 1)) : (size_t)k;
+        size_t at = PACKED ? (size_t)(k >> lay.log2Block) * lay.blockPitch + (k & ((1 << lay.log2Block) - 1)) : (size_t)k;
+        if (peers) {
+            // peer-memory transpose: block k >> log2Block goes straight to its owner, at [global row j][slot in block]
+            rowA = lay.peerTable[k >> lay.log2Block] + (size_t)j * lay.rowPitch;
+            rowB = rowA + lay.rowPitch;
+            at = (size_t)(k & ((1 << lay.log2Block) - 1));
+        }
         if (k == 0) {
             const float2 zn = v[8];                // Z[N/2] (tt = 0): both rows real
-            rowA[0] = make_float2(2.0f * scale * zn.x, 0.0f);
-            rowB[0] = make_float2(2.0f * scale * zn.y, 0.0f);
+            rowA[at] = make_float2(2.0f * scale * zn.x, 0.0f);
+            rowB[at] = make_float2(2.0f * scale * zn.y, 0.0f);
         } else {
             const float2 zk = v[m], zc = buf[fft::pad(N - k)];
             // A_k = (Z_k + conj Z_{N-k}) / 2,  B_k = (Z_k - conj Z_{N-k}) / (2i)

@@ -162,7 +162,7 @@ __global__ void buildBandSolveTablesKernel(GridParams g, SpectralTables t, Spect
 // are in flight together and the only dependent chains are the FMA recurrences themselves.
 template <int W, int L, int P>
 __global__ void __launch_bounds__(P * W)
-tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int pitch, int groupOffset)
+tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int pitch, int groupOffset, PeerScatter scatter)
 {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int nT = P * L;
@@ -310,26 +310,38 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
         const float dl = kPrefetch ? de[k] : __ldg(tabDelta + item);
         const float2 gm = d[q * kChunkPitch + (i % L) * W + ww];
         const float2 xn = carryX[(q + 1) * W + ww];
-        spectrum[(size_t)i * half + ww] = make_float2(__fmaf_rn(dl, xn.x, gm.x), __fmaf_rn(dl, xn.y, gm.y));
+        const float2 x = make_float2(__fmaf_rn(dl, xn.x, gm.x), __fmaf_rn(dl, xn.y, gm.y));
+        if (scatter.table) {
+            // peer-memory transpose (dist.cu): straight into the owner of row i, in the layout its inverse FFT reads
+            const int rows = 1 << scatter.log2Rows;
+            const int dest = i >> scatter.log2Rows, local = i & (rows - 1);
+            const size_t blockPitch = (size_t)(rows + 1) * scatter.kper;
+            const size_t at = (size_t)scatter.myRank * blockPitch + (size_t)blockIdx.x * W + ww;
+            scatter.table[dest][at + (size_t)local * scatter.kper] = x;
+            if (local == 0 && dest > 0) scatter.table[dest - 1][at + (size_t)rows * scatter.kper] = x;    // the extra row of the band above
+        } else {
+            spectrum[(size_t)i * half + ww] = x;
+        }
     }
 }
 
 template <int W, int L, int P>
 cudaError_t launchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, const TriLaunch& l,
-                      cudaStream_t stream, bool configureOnly, int pitch, int slotBegin, int slotCount)
+                      cudaStream_t stream, bool configureOnly, int pitch, int slotBegin, int slotCount, const PeerScatter& scatter)
 {
     if (configureOnly)
         return cudaFuncSetAttribute(tridiagonalKernel<W, L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
     if (slotBegin % W != 0 || slotCount % W != 0) return cudaErrorInvalidValue;
     dim3 grid(slotCount / W, batch);
-    return launchChained(tridiagonalKernel<W, L, P>, grid, dim3(P * W), l.smem, stream, g, t, spectrum, pitch, slotBegin / W);
+    return launchChained(tridiagonalKernel<W, L, P>, grid, dim3(P * W), l.smem, stream, g, t, spectrum, pitch, slotBegin / W, scatter);
 }
 
 cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
-                        cudaStream_t stream, bool configureOnly, int tableBatch, int pitch, int slotBegin, int slotCount)
+                        cudaStream_t stream, bool configureOnly, int tableBatch, int pitch, int slotBegin, int slotCount,
+                        const PeerScatter& scatter = PeerScatter{})
 {
     const TriLaunch l = triLaunch(g, tableBatch);      // the tables were laid out for this W at creation
-#define KB_TRI(WW, LL, PP) if (l.W == WW && l.L == LL && l.P == PP) return launchTri<WW, LL, PP>(g, t, spectrum, batch, l, stream, configureOnly, pitch, slotBegin, slotCount)
+#define KB_TRI(WW, LL, PP) if (l.W == WW && l.L == LL && l.P == PP) return launchTri<WW, LL, PP>(g, t, spectrum, batch, l, stream, configureOnly, pitch, slotBegin, slotCount, scatter)
 #define KB_TRI_W(LL, PP) KB_TRI(2, LL, PP); KB_TRI(4, LL, PP); KB_TRI(8, LL, PP)
     KB_TRI_W(4, 4); KB_TRI_W(4, 8); KB_TRI_W(4, 16);          // nTheta = 16, 32, 64
     KB_TRI_W(8, 16); KB_TRI_W(8, 32);                         // 128, 256
@@ -374,9 +386,9 @@ cudaError_t launchTridiagonal(const GridParams& g, const SpectralTables& t, floa
 }
 
 cudaError_t launchTridiagonalBand(const GridParams& g, const SpectralTables& t, float2* packed, int pitch,
-                                  int slotBegin, int slotCount, int tableBatch, cudaStream_t stream)
+                                  int slotBegin, int slotCount, int tableBatch, cudaStream_t stream, const PeerScatter* scatter)
 {
-    return dispatchTri(g, t, packed, 1, stream, false, tableBatch, pitch, slotBegin, slotCount);
+    return dispatchTri(g, t, packed, 1, stream, false, tableBatch, pitch, slotBegin, slotCount, scatter ? *scatter : PeerScatter{});
 }
 
 // ---- band-local solve (reduced-interface / SPIKE mode of the band-decomposed run) -------------------

@@ -70,6 +70,13 @@ class _Rank:
         self.upload(capi.VEL_THETA, v[:self.rows_of(capi.VEL_THETA)])
         return u, v
 
+    def transport(self, peer_stores=None):
+        """-> (uses peer-memory transposes, note). peer_stores = True / False switches (collective over the ranks)."""
+        uses, note = ctypes.c_int(), ctypes.c_char_p()
+        _check(self.lib.kamino_dist_transport(self.handle, -1 if peer_stores is None else int(bool(peer_stores)),
+                                              ctypes.byref(uses), ctypes.byref(note)), self.handle)
+        return bool(uses.value), (note.value or b"").decode()
+
     def init_velocity_on_device(self):
         _check(self.lib.kamino_dist_init_velocity_device(self.handle), self.handle)
 
@@ -138,9 +145,14 @@ class DistributedSolver(_Rank):
 class LocalGroup:
     """P virtual ranks in one process on one device (kamino_dist_group_step)."""
 
-    def __init__(self, nTheta, radius, dt, world, device=0):
+    def __init__(self, nTheta, radius, dt, world, device=0, peer_stores=False):
+        """peer_stores: the kernels store straight into the sibling ranks' buffers (the peer-memory transposes of the
+        NCCL ranks) instead of staging + device copies."""
         self.ranks = [_Rank(nTheta, radius, dt, r, world, device, None) for r in range(world)]
         self.world, self.nTheta, self.nPhi = world, nTheta, 2 * nTheta
+        if peer_stores and world > 1:
+            for r in self.ranks:
+                assert r.transport(True)[0]
         self._handles = (ctypes.c_void_p * world)(*[r.handle for r in self.ranks])
 
     def close(self):

@@ -65,19 +65,30 @@ def main():
     d.sync()
     got = {f: d.download(f) for f in (capi.VEL_PHI, capi.VEL_THETA, capi.DENSITY)}
     finite = all(np.isfinite(a).all() for a in got.values())
-    # timing: `timed` more steps, max over ranks
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    d.step(timed)
-    d.sync()
-    dist.barrier()
-    ms_dist = (time.perf_counter() - t0) / timed * 1e3
+    # timing: `timed` more steps, max over ranks; then the same with the other transport of the transposes
+    def timed_run():
+        d.step(2); d.sync()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d.step(timed)
+        d.sync()
+        dist.barrier()
+        return (time.perf_counter() - t0) / timed * 1e3
+    peer, note = d.transport()
+    ms_dist = timed_run()
+    ms_other = None
+    if world > 1 and (peer or "IPC mappings" in note):
+        d.transport(not peer)
+        ms_other = timed_run()
+        d.transport(peer)
     d.comm_stats(enable=1)
     d.step(timed)
     d.sync()
     stats = d.comm_stats(enable=0)
-    line = "rank %d/%d nTheta %d rows [%d,%d) %.2f GB on device, init %.1f s, finite %s, %.3f ms/step banded" % (
-        rank, world, nT, d.lo, d.hi, d.device_bytes / 1e9, t_init, finite, ms_dist)
+    line = "rank %d/%d nTheta %d rows [%d,%d) %.2f GB on device, init %.1f s, finite %s, %.3f ms/step banded (%s; %s)" % (
+        rank, world, nT, d.lo, d.hi, d.device_bytes / 1e9, t_init, finite, ms_dist, "peer stores" if peer else "NCCL transposes", note)
+    if ms_other is not None:
+        line += ", %.3f ms/step with %s" % (ms_other, "NCCL transposes" if peer else "peer stores")
     if stats["steps"]:
         n = stats["steps"]
         line += " | halo %.3f ms (%.1f GB/s) transposes %.3f ms (%.1f GB/s sent)" % (

@@ -670,15 +670,18 @@ def _single_gpu_steps(K, nT, steps, scale=1.0):
     return u0, v0, rho0, st, pr
 
 
+@pytest.mark.parametrize("peer_stores", [False, True], ids=["staged", "peer-stores"])
 @pytest.mark.parametrize("nT,world", [(128, 4), (256, 2), (512, 8), (128, 1)])
-def test_dist_virtual_ranks_bit_identical_to_single_gpu(K, nT, world):
+def test_dist_virtual_ranks_bit_identical_to_single_gpu(K, nT, world, peer_stores):
     """kamino_dist_*: band-sized buffers, the FFTs writing / reading the transposes' wire layouts, the theta
     solve on the rank's wavenumber band with band-only LU tables. P virtual ranks on one device
-    (kamino_dist_group_step: device copies where the NCCL ranks send / receive) against kamino_step:
-    u_phi, u_theta, density and pressure bit-identical after 3 steps."""
+    (kamino_dist_group_step) against kamino_step: u_phi, u_theta, density and pressure bit-identical after 3 steps.
+    Both transports of the transposes: staged buffers moved by device copies (where the NCCL ranks send / receive), and
+    peer stores (the FFT kernel and the theta solve write straight into the sibling ranks' buffers, as the NCCL ranks do
+    through CUDA IPC mappings)."""
     from kaminogpu_b200 import capi, dist
     u0, v0, rho0, st, pr = _single_gpu_steps(K, nT, 3)
-    grp = dist.LocalGroup(nT, 5.0, 0.005, world)
+    grp = dist.LocalGroup(nT, 5.0, 0.005, world, peer_stores=peer_stores)
     try:
         grp.upload_global(capi.VEL_PHI, u0)
         grp.upload_global(capi.VEL_THETA, v0)
@@ -694,7 +697,7 @@ def test_dist_virtual_ranks_bit_identical_to_single_gpu(K, nT, world):
     want = dict(st, pressure=pr)
     for name in ("velPhi", "velTheta", "density", "pressure"):
         w = words_equal(got[name], want[name])
-        print("dist x%d nTheta %d %-9s identical words %.6f" % (world, nT, name, w))
+        print("dist x%d nTheta %d %s %-9s identical words %.6f" % (world, nT, "peer-stores" if peer_stores else "staged", name, w))
         assert np.array_equal(got[name].ravel().view(np.uint32), np.asarray(want[name], np.float32).ravel().view(np.uint32)), name
     if world > 1:
         # band-sized memory: a rank holds (rows + 2 x 24 halo) rows of 7 field buffers, 3 spectrum buffers, 1/P of the tables
