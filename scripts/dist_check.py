@@ -91,9 +91,13 @@ def main():
         line += ", %.3f ms/step with %s" % (ms_other, "NCCL transposes" if peer else "peer stores")
     if stats["steps"]:
         n = stats["steps"]
-        line += " | halo %.3f ms (%.1f GB/s) transposes %.3f ms (%.1f GB/s sent)" % (
-            stats["halo_s"] / n * 1e3, stats["halo_bytes_per_step"] / max(stats["halo_s"] / n, 1e-9) / 1e9,
-            stats["transpose_s"] / n * 1e3, stats["transpose_bytes_per_step"] / max(stats["transpose_s"] / n, 1e-9) / 1e9)
+        line += " | halo %.3f ms (%.1f GB/s)" % (stats["halo_s"] / n * 1e3, stats["halo_bytes_per_step"] / max(stats["halo_s"] / n, 1e-9) / 1e9)
+        if peer:
+            line += " barriers of the peer-store transposes %.3f ms (%.1f MB stored into peers per step)" % (
+                stats["transpose_s"] / n * 1e3, stats["transpose_bytes_per_step"] / 1e6)
+        else:
+            line += " transposes %.3f ms (%.1f GB/s sent)" % (
+                stats["transpose_s"] / n * 1e3, stats["transpose_bytes_per_step"] / max(stats["transpose_s"] / n, 1e-9) / 1e9)
     # single-GPU run of the whole grid on this rank's GPU, compared on my band
     same = None
     try:
