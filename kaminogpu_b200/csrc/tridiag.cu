@@ -160,7 +160,11 @@ __global__ void buildBandSolveTablesKernel(GridParams g, SpectralTables t, Spect
 // the 64-bit accesses of a half-warp (16 / W chunks x W systems) then fall in distinct banks.
 // W, L and P are compile-time so that every loop is fully unrolled: all global loads of a phase
 // are in flight together and the only dependent chains are the FMA recurrences themselves.
-template <int W, int L, int P>
+// SCATTER (theta-band runs with peer-memory transposes, dist.cu): the solution is not written back in place but straight
+// into the owning ranks' buffers. A compile-time variant: the in-place kernel keeps exactly the code (and SASS) it had
+// before -- a run-time branch around the store made the pointer-table stores alias-block the table loads of the unrolled
+// loop (r02r ncu at 2048 x 4096: 68 instead of 48 us).
+template <int W, int L, int P, bool SCATTER>
 __global__ void __launch_bounds__(P * W)
 tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumAll, int pitch, int groupOffset, PeerScatter scatter)
 {
@@ -302,25 +306,47 @@ tridiagonalKernel(GridParams g, SpectralTables t, float2* __restrict__ spectrumA
     }
     __syncthreads();
     // x_i = gamma_i + delta_i X_{p+1}, written back in the load mapping (coalesced)
+    if constexpr (!SCATTER) {
 #pragma unroll(kPrefetch ? L : 8)
-    for (int k = 0; k < L; ++k) {
-        const int item = tid + k * kThreads;
-        const int i = item / W, ww = item % W;
-        const int q = i / L;
-        const float dl = kPrefetch ? de[k] : __ldg(tabDelta + item);
-        const float2 gm = d[q * kChunkPitch + (i % L) * W + ww];
-        const float2 xn = carryX[(q + 1) * W + ww];
-        const float2 x = make_float2(__fmaf_rn(dl, xn.x, gm.x), __fmaf_rn(dl, xn.y, gm.y));
-        if (scatter.table) {
-            // peer-memory transpose (dist.cu): straight into the owner of row i, in the layout its inverse FFT reads
-            const int rows = 1 << scatter.log2Rows;
-            const int dest = i >> scatter.log2Rows, local = i & (rows - 1);
-            const size_t blockPitch = (size_t)(rows + 1) * scatter.kper;
-            const size_t at = (size_t)scatter.myRank * blockPitch + (size_t)blockIdx.x * W + ww;
-            scatter.table[dest][at + (size_t)local * scatter.kper] = x;
-            if (local == 0 && dest > 0) scatter.table[dest - 1][at + (size_t)rows * scatter.kper] = x;    // the extra row of the band above
-        } else {
-            spectrum[(size_t)i * half + ww] = x;
+        for (int k = 0; k < L; ++k) {
+            const int item = tid + k * kThreads;
+            const int i = item / W, ww = item % W;
+            const int q = i / L;
+            const float dl = kPrefetch ? de[k] : __ldg(tabDelta + item);
+            const float2 gm = d[q * kChunkPitch + (i % L) * W + ww];
+            const float2 xn = carryX[(q + 1) * W + ww];
+            spectrum[(size_t)i * half + ww] = make_float2(__fmaf_rn(dl, xn.x, gm.x), __fmaf_rn(dl, xn.y, gm.y));
+        }
+    } else {
+        // peer-memory transpose: row i goes straight to its owner, in the layout the owner's inverse FFT reads
+        // ([source rank][rows + 1][K]); the first row of a band is also the extra row of the band above it. The values
+        // of a batch are computed first (all table loads in flight together), then stored: the stores go through
+        // pointers the compiler cannot prove distinct from the tables.
+        const int rows = 1 << scatter.log2Rows;
+        const size_t blockPitch = (size_t)(rows + 1) * scatter.kper;
+        constexpr int kOut = L < 8 ? L : 8;
+#pragma unroll 1
+        for (int k0 = 0; k0 < L; k0 += kOut) {
+            float2 x[kOut];
+#pragma unroll
+            for (int u = 0; u < kOut; ++u) {
+                const int item = tid + (k0 + u) * kThreads;
+                const int i = item / W, ww = item % W;
+                const int q = i / L;
+                const float dl = __ldg(tabDelta + item);
+                const float2 gm = d[q * kChunkPitch + (i % L) * W + ww];
+                const float2 xn = carryX[(q + 1) * W + ww];
+                x[u] = make_float2(__fmaf_rn(dl, xn.x, gm.x), __fmaf_rn(dl, xn.y, gm.y));
+            }
+#pragma unroll
+            for (int u = 0; u < kOut; ++u) {
+                const int item = tid + (k0 + u) * kThreads;
+                const int i = item / W, ww = item % W;
+                const int dest = i >> scatter.log2Rows, local = i & (rows - 1);
+                const size_t at = (size_t)scatter.myRank * blockPitch + (size_t)blockIdx.x * W + ww;
+                scatter.table[dest][at + (size_t)local * scatter.kper] = x[u];
+                if (local == 0 && dest > 0) scatter.table[dest - 1][at + (size_t)rows * scatter.kper] = x[u];
+            }
         }
     }
 }
@@ -329,11 +355,16 @@ template <int W, int L, int P>
 cudaError_t launchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch, const TriLaunch& l,
                       cudaStream_t stream, bool configureOnly, int pitch, int slotBegin, int slotCount, const PeerScatter& scatter)
 {
-    if (configureOnly)
-        return cudaFuncSetAttribute(tridiagonalKernel<W, L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+    if (configureOnly) {
+        cudaError_t e = cudaFuncSetAttribute(tridiagonalKernel<W, L, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(tridiagonalKernel<W, L, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+    }
     if (slotBegin % W != 0 || slotCount % W != 0) return cudaErrorInvalidValue;
     dim3 grid(slotCount / W, batch);
-    return launchChained(tridiagonalKernel<W, L, P>, grid, dim3(P * W), l.smem, stream, g, t, spectrum, pitch, slotBegin / W, scatter);
+    if (scatter.table)
+        return launchChained(tridiagonalKernel<W, L, P, true>, grid, dim3(P * W), l.smem, stream, g, t, spectrum, pitch, slotBegin / W, scatter);
+    return launchChained(tridiagonalKernel<W, L, P, false>, grid, dim3(P * W), l.smem, stream, g, t, spectrum, pitch, slotBegin / W, scatter);
 }
 
 cudaError_t dispatchTri(const GridParams& g, const SpectralTables& t, float2* spectrum, int batch,
