@@ -35,6 +35,10 @@ import numpy as np
 from . import capi
 from .solver import KaminoSolver
 
+# NOTE: this module is the Python RESEARCH PROTOTYPE of the band decomposition (kept as the vehicle of the reduced-interface
+# "SPIKE" theta solve). The product path is C++: csrc/dist.cu behind kamino_dist_* (kaminogpu_b200/dist.py mirrors it), with
+# band-sized buffers, peer-memory / NCCL transposes and a device-side check that no backtrace leaves the halo. Here every
+# rank keeps full-size buffers and the halo width is only checked on the host (check_halo below).
 HALO = 24          # rows exchanged with each neighbour
 ADVECT_EXTRA = 16  # rows beyond the band that the advection recomputes
 GEO_EXTRA = 8      # rows beyond the band that the geometric phase recomputes
@@ -412,9 +416,21 @@ class DistributedBandedSolver:
     def sync(self):
         self.stream.synchronize()
 
+    def check_halo(self):
+        """Raise if the theta displacement of a backtrace can leave the exchanged halo (r01 ADVICE: it used to read stale
+        rows silently): max |u_theta| dt / (R h) rows per stage, two stages, plus the bilinear stencil."""
+        r = self.r
+        v = r.fields()[1]
+        rows = float(v[max(r.lo - 1, 0):r.hi].abs().max()) * r.solver.frameDuration / (r.solver.radius * float(r.solver.gridLen))
+        if 2.0 * rows + 2.0 > HALO - ADVECT_EXTRA:
+            raise RuntimeError("theta-CFL %.2f rows per stage: a backtrace can leave the %d-row halo of the band decomposition"
+                               % (rows, HALO))
+
     def _step(self, nSteps):
         r, dist = self.r, self.dist
-        for _ in range(nSteps):
+        for k in range(nSteps):
+            if self.world > 1 and k % 8 == 0:
+                self.check_halo()
             if self.world > 1:
                 exchange(r.halo_sends(), r.halo_recvs(), dist)
             r.advect_to_spectrum()
