@@ -574,6 +574,37 @@ def test_cli_runs_config_file(K, tmp_path):
             assert version == 5 and points == npts
 
 
+@pytest.mark.timeout(600)
+def test_reference_executable_and_drop_in_on_the_shipped_scenario(K, tmp_path):
+    """BASELINE config 1 through the executables: the reference's own `main` (oracle/_ref/kamino_ref_exe: all nine
+    reference TUs incl. kernel/main.cu, Partio / OpenCV replaced by the link shim, i.e. output off) and the drop-in
+    `kamino` on the same configKamino.txt -- the Kamino defaults of include/KaminoGPU.cuh:40-44: 128 x 256, particle
+    density 200 (6,552,200 particles), dt 0.005, 10 frames of 1/24 s (100 steps). Both must run to completion and
+    announce the same frames; the drop-in's step count per frame is the reference's loop rule
+    (kernel/KaminoCore.cu:886-895). State-level parity at this size is test_live_reference_build_at_baseline_sizes[c1]."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_exe = os.path.join(root, "oracle", "_ref", "kamino_ref_exe")
+    if not os.path.exists(ref_exe):
+        pytest.skip("oracle/_ref/kamino_ref_exe not built (needs /root/reference at build time)")
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "ours").mkdir()
+    tokens = "5.0 128 200.0 0.005 0.041666668 10 0.0 1 1 1 1 %s %s null null null\n"
+    (tmp_path / "ref" / "configKamino.txt").write_text(tokens % ("f", "p"))            # the shim's Partio::write is a no-op
+    (tmp_path / "ours" / "configKamino.txt").write_text(tokens % ("null", "null"))     # output off
+    ref = subprocess.run([ref_exe, "configKamino.txt"], cwd=str(tmp_path / "ref"), capture_output=True, text=True, timeout=400)
+    assert ref.returncode == 0, ref.stderr[-500:]
+    ours = subprocess.run([os.path.join(root, "kaminogpu_b200", "kamino"), "configKamino.txt"], cwd=str(tmp_path / "ours"),
+                          capture_output=True, text=True, timeout=400)
+    assert ours.returncode == 0, ours.stderr[-500:]
+    frames = lambda out: [l.strip() for l in out.splitlines() if l.startswith("Frame ")]
+    assert frames(ref.stdout) == frames(ours.stdout) == ["Frame %d is ready" % i for i in range(1, 11)]
+    for out in (ref.stdout, ours.stdout):
+        assert "Initializing velocity..." in out and "frames per second" in out
+    assert sum(K.steps_per_frame(0.005, 0.041666668, 10)) == 100
+
+
 def test_cli_image_driven_initialisation(K, tmp_path):
     """densityImage / colorImage tokens of configKamino.txt (kernel/main.cu:40-45): the density and the
     particle colours come from the mirrored, resized image (kernel/KaminoSolver.cu:243-277,
