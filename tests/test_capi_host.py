@@ -30,6 +30,28 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
 
 
+def test_header_is_plain_c(built, tmp_path):
+    """The drop-in boundary is a C ABI: include/kamino_b200.h must compile as C99 with nothing but the standard headers
+    (no CUDA, torch or C++ types in any signature), and a C program must link against the library by symbol name."""
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "kamino_b200.h"\n'
+                   'int main(void) {\n'
+                   '    kamino_ctx* c = 0; kamino_dist* d = 0; unsigned char id[128];\n'
+                   '    int rc = kamino_create(&c, 0, 7, 5.0f, 0.005f, 1, 0);          /* nTheta = 7: rejected before any device work */\n'
+                   '    if (rc != KAMINO_ERR_INVALID || c != 0) return 1;\n'
+                   '    rc = kamino_dist_create(&d, 0, 100, 5.0f, 0.005f, 0, 1, id);\n'
+                   '    if (rc != KAMINO_ERR_INVALID || d != 0) return 2;\n'
+                   '    return kamino_version()[0] == \'k\' ? 0 : 3;\n'
+                   '}\n')
+    exe = tmp_path / "cabi"
+    pkg = os.path.join(ROOT, "kaminogpu_b200")
+    build = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                            "-o", str(exe), "-L" + pkg, "-lkamino_b200", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stderr)
+
+
 def test_library_is_sm100a_only(built):
     out = subprocess.run(["cuobjdump", "-lelf", built], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
